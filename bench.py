@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""Benchmark of the KPP chemistry hot path (BASELINE.json metric:
+"KPP cell-integrations/sec (gas+aer) at 1/2/4/8 B200 vs host-CPU reference").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                  [--cols C] [--mechs gas[,aer[,tot]]]
+
+One "step" = one INTEGRATE call (t = 0 -> 10 s, reference options) over every cell
+of the rank's synthetic ensemble (C columns x 148 cells of the gas
+mechanism, plus the aqueous batches when requested), restarted from the same
+saved spun-up state.  Weak scaling: every rank owns its own C columns; no
+data-path collective, NCCL only reduces the diagnostics.
+
+Prints ONE JSON line on rank 0 (contract in the task statement): `value` =
+device-resident throughput, `e2e` = the same through the host-buffer C-ABI call
+with H2D/D2H inside the timed region, `roofline` for the dominant kernel,
+`cpu_baseline` = the CPU oracle (C restatement of the reference path; the
+Fortran reference cannot be built in this image) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "kpp_cell_integrations_per_s"
+UNIT = "cell-integrations/s"
+MECH_ID = {"gas": 0, "aer": 1, "tot": 2}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cols", type=int, default=int(os.environ.get("MISTRA_BENCH_COLS", "10000")),
+                    help="columns per GPU (148 cells each)")
+    ap.add_argument("--mechs", default=os.environ.get("MISTRA_BENCH_MECHS", "gas"))
+    ap.add_argument("--spinup", type=int, default=int(os.environ.get("MISTRA_BENCH_SPINUP", "12")))
+    ap.add_argument("--cpu-sample-cols", type=int, default=96)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------
+def build_ensemble(mech, cols, rank, spinup, use_gpu):
+    """Synthetic per-rank ensemble, spun up so that the timed step sees a stiff
+    quasi-steady radical state.  Spin-up uses the CUDA path when a GPU is present
+    (it is input preparation, not part of the timed region)."""
+    from mistra_b200 import synthetic
+    if mech != "gas":
+        raise SystemExit("bench: synthetic inputs for mechanism %r are not available yet" % mech)
+    ens = synthetic.GasEnsemble(cols, col0=rank * cols)
+    var = ens.var
+    rc = ens.rconst(var)
+    if spinup > 0:
+        if use_gpu:
+            from mistra_b200 import kpp
+            for s in range(spinup):
+                if s and s % 6 == 0:
+                    rc = ens.rconst(var)
+                var, ierr, _, _, _ = kpp.integrate(MECH_ID[mech], rc, ens.fix, var)
+        else:
+            from oracle import kpp_oracle as ko
+            for s in range(spinup):
+                if s and s % 6 == 0:
+                    rc = ens.rconst(var)
+                var = ko.integrate(MECH_ID[mech], rc, ens.fix, var, nthreads=os.cpu_count() or 1)[0]
+        rc = ens.rconst(var)
+    return ens, np.ascontiguousarray(var), np.ascontiguousarray(rc), np.ascontiguousarray(ens.fix)
+
+
+def cpu_baseline(mech, var, rc, fix, ncells, threads):
+    """CPU oracle (kind 'port': C restatement of the reference Fortran) on a
+    bounded sample of the same workload."""
+    from oracle import kpp_oracle as ko
+    n = min(ncells, var.shape[0])
+    t0 = time.perf_counter()
+    _, ierr, stats, _, _ = ko.integrate(MECH_ID[mech], rc[:n], fix[:n], var[:n], nthreads=threads)
+    dt = time.perf_counter() - t0
+    return n / dt, dt, stats
+
+
+# ----------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path, i.e.
+    the oracle port (no Fortran compiler in this image), all host threads, on a
+    bounded sample of the same workload.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    mech = args.mechs.split(",")[0]
+    cols = args.cpu_sample_cols
+    ens, var, rc, fix = build_ensemble(mech, cols, 0, min(args.spinup, 4), use_gpu=False)
+    n = var.shape[0]
+    for _ in range(args.warmup):
+        cpu_baseline(mech, var, rc, fix, n, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rate, dt, stats = cpu_baseline(mech, var, rc, fix, n, threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "synthetic Mistra ensemble, %s mechanism, Ros3 0->10 s" % mech,
+                   "sample": "%d columns x 148 cells = %d cells per step" % (cols, n)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d cells (%d columns), OpenMP over cells" % (n, cols)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from mistra_b200 import kpp
+    from mistra_b200.mechgen import mech as mechmod
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    mechs = args.mechs.split(",")
+    batches = []
+    for mname in mechs:
+        ens, var, rc, fix = build_ensemble(mname, args.cols, rank, args.spinup, use_gpu=True)
+        batches.append((mname, var, rc, fix))
+    ncell_rank = sum(b[1].shape[0] for b in batches)
+
+    # ---- device-resident arm --------------------------------------------------
+    stream = torch.cuda.current_stream()
+    dbatches = []
+    for mname, var, rc, fix in batches:
+        n = var.shape[0]
+        d = {
+            "mech": MECH_ID[mname], "name": mname, "n": n,
+            "var0": torch.from_numpy(var).to(dev), "var": torch.empty((n, var.shape[1]), dtype=torch.float64, device=dev),
+            "rc": torch.from_numpy(rc).to(dev), "fix": torch.from_numpy(fix).to(dev),
+            "ierr": torch.zeros(n, dtype=torch.int32, device=dev),
+            "stats": torch.zeros((n, 8), dtype=torch.int32, device=dev),
+            "hexit": torch.zeros(n, dtype=torch.float64, device=dev),
+        }
+        dbatches.append(d)
+
+    kev = []  # (mech name, start event, end event) around each kernel launch of the timed steps
+
+    def step_device(timed):
+        for d in dbatches:
+            d["var"].copy_(d["var0"])
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            kpp.integrate_device(d["mech"], d["rc"], d["fix"], d["var"], 0.0, 10.0, ierr=d["ierr"],
+                                 stats=d["stats"], hexit=d["hexit"])
+            e1.record(stream)
+            if timed:
+                kev.append((d["name"], e0, e1))
+
+    for _ in range(args.warmup):
+        step_device(False)
+    barrier()
+    l0 = kpp.launch_count()
+    with ClockSampler(local) as clk:
+        t_start = torch.cuda.Event(enable_timing=True)
+        t_end = torch.cuda.Event(enable_timing=True)
+        t_start.record(stream)
+        for _ in range(args.steps):
+            step_device(True)
+        t_end.record(stream)
+        barrier()
+    launches = kpp.launch_count() - l0
+    ms_total = t_start.elapsed_time(t_end)
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tmax.item()) / args.steps
+    total_cells = ncell_rank * world
+    value = total_cells / (ms_per_step * 1e-3)
+
+    # diagnostics (the only collective on the path): sum of steps / rejects / failures
+    diag = torch.zeros(4, dtype=torch.float64, device=dev)
+    flops_rank = 0.0
+    kernel_ms = {}
+    for d in dbatches:
+        st = d["stats"].double()
+        diag[0] += st[:, 2].sum()
+        diag[1] += st[:, 4].sum()
+        diag[2] += (d["ierr"] != 1).sum()
+        diag[3] += d["n"]
+        m = mechmod.load(d["name"])
+        d["flops"] = float(m.flops_from_stats(d["stats"].cpu().numpy()))
+        flops_rank += d["flops"]
+    for name, e0, e1 in kev:
+        kernel_ms.setdefault(name, []).append(e0.elapsed_time(e1))
+    if world > 1:
+        dist.all_reduce(diag, op=dist.ReduceOp.SUM)
+
+    # ---- roofline of the dominant kernel (rank 0's launches) -------------------
+    dom = max(kernel_ms, key=lambda k: sum(kernel_ms[k]))
+    dd = [d for d in dbatches if d["name"] == dom][0]
+    kms = float(np.mean(kernel_ms[dom]))
+    fp64_peak = kpp.fp64_peak_tflops()
+    peaks, peak_src = measured_peaks()
+    mdom = mechmod.load(dom)
+    io_bytes = mdom.io_bytes * dd["n"]
+    roof = {
+        "bound": "fp64", "kernel": "ros3_kernel_%s" % mdom.suffix,
+        "achieved": dd["flops"] / (kms * 1e-3) * 1e-12, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": dd["flops"] / (kms * 1e-3) * 1e-12 / fp64_peak,
+        "peak_source": "measured live: 8-chain DFMA microbenchmark (MEASURED_PEAKS.json has no FP64 entry)",
+        "flops_per_launch": dd["flops"], "kernel_ms": kms, "traffic": None,
+        "note": "algorithmic flops of the reference formulation from the integrator's own counters "
+                "(SURVEY.md 8d; FMA=2, div=1; includes the dF/dT Fun call this kernel skips)",
+        "hbm": {"bound": "hbm", "achieved": io_bytes / (kms * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": io_bytes / (kms * 1e-3) * 1e-9 / peaks["hbm_gbs"],
+                "peak_source": peak_src,
+                "note": "compulsory I/O only: (2*NVAR+NFIX+NREACT)*8 B per cell-integration"},
+    }
+
+    # ---- end-to-end arm: host buffers through the C-ABI call --------------------
+    e2e = None
+    if not args.no_e2e:
+        hb = []
+        for mname, var, rc, fix in batches:
+            hv0 = torch.from_numpy(var).pin_memory()
+            hb.append((MECH_ID[mname], hv0, torch.empty_like(hv0).pin_memory(),
+                       torch.from_numpy(rc).pin_memory(), torch.from_numpy(fix).pin_memory()))
+        h2d = sum(v0.numel() * 8 + r.numel() * 8 + f.numel() * 8 for _, v0, _, r, f in hb)
+        d2h = sum(v0.numel() * 8 + v0.shape[0] * (4 + 32 + 8) for _, v0, _, r, f in hb)
+
+        def step_host():
+            acc = 0
+            for mech, v0, v, r, f in hb:
+                _, ierr, stats, hexit, _tx = kpp.integrate(mech, r.numpy(), f.numpy(), v0.numpy(), out=v.numpy())
+                acc += int((ierr != 1).sum())
+            return acc
+        for _ in range(max(1, args.warmup - 1)):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_cells / (float(tt.item()) / args.steps), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": float(tt.item()) / args.steps * 1e3}
+
+    # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        mname, var, rc, fix = batches[0]
+        n_all = min(var.shape[0], args.cpu_sample_cols * 148 * max(1, threads // 4))
+        cpu_baseline(mname, var, rc, fix, 2048, threads)           # warm-up
+        r_all, dt_all, _ = cpu_baseline(mname, var, rc, fix, n_all, threads)
+        n_1 = min(var.shape[0], 8 * 148)
+        r_1, dt_1, _ = cpu_baseline(mname, var, rc, fix, n_1, 1)
+        cpu = {"value": r_all, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d %s cells, OpenMP over cells, %.1f s" % (n_all, mname, dt_all),
+               "value_1thread": r_1, "sample_1thread": "%d cells, %.1f s" % (n_1, dt_1),
+               "note": "C restatement of the reference Fortran (no Fortran compiler in the image)"}
+
+    if rank == 0:
+        clocks = clk.summary()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic ensemble of independent Mistra columns (SURVEY 8d), "
+                                   "%d columns x 148 cells per GPU, mechanisms: %s; Ros3 0->10 s, "
+                                   "RTOL 1e-3 ATOL 1e-25 Hstart 1e-3" % (args.cols, "+".join(mechs)),
+                       "cells_per_gpu": ncell_rank, "columns_per_gpu": args.cols,
+                       "parallelism": "cells sharded by column over %d GPU(s), no data-path collective" % world,
+                       "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no explicit flush"
+                             % (sum(d["rc"].numel() * 8 + d["var"].numel() * 8 for d in dbatches) * 1e-9)},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roof, "cpu_baseline": cpu,
+            "diagnostics": {"sum_nstp": float(diag[0]), "sum_nrej": float(diag[1]),
+                            "failed_cells": float(diag[2]), "cells": float(diag[3]),
+                            "mean_steps_per_cell": float(diag[0] / max(1.0, float(diag[3])))},
+            "per_mechanism": {k: {"kernel_ms": float(np.mean(v)),
+                                  "cells_per_s": [d["n"] for d in dbatches if d["name"] == k][0] / (np.mean(v) * 1e-3)}
+                              for k, v in kernel_ms.items()},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

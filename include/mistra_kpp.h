@@ -1,0 +1,120 @@
+/* mistra_kpp.h - C ABI of the B200 KPP chemistry path (libmistra_kpp.so).
+ *
+ * Drop-in boundary for the reference's stiff-chemistry hot path
+ * (SURVEY.md §8b).  The reference has no plugin/FFI interface; the path sits
+ * behind Fortran external procedures and COMMON blocks, so the boundary is cut at
+ * the two places a maintainer can splice a C call in:
+ *
+ *   B2 (batched, the throughput path): replaces the per-layer body
+ *      "Update_RCONST_x ; INTEGRATE_x(tkpp, tkpp+dt_ch)" of the k-loop of
+ *      kpp_driver (/root/reference/src/kpp.f90:4310-4470, dispatch 4451-4468;
+ *      call sites gas.f:172-173, aer.f:216-217, tot.f:603-604).  The host keeps
+ *      gathering C/FIX and computing RCONST per cell exactly as today, stacks
+ *      them for all layers of a mechanism, and makes ONE call.
+ *
+ *   B1 (per-cell link-level shim, see mistra_kpp_f77.h): replaces
+ *      INTEGRATE_g/_a/_t(TIN,TOUT) (gas.f:710, aer.f:1408, tot.f:2812).
+ *
+ * Species order = ind_* of *_Parameters.h, reaction order = RCONST(1:NREACT) of
+ * Update_RCONST_x, sparse order = LU_* of *_Sparse.h (all reproduced from the
+ * reference's generated sources; check with mistra_kpp_spc_name).
+ *
+ * All functions return 0 on success or a negative MISTRA_KPP_E* code; the text
+ * of the last error is available from mistra_kpp_last_error().  There is no CPU
+ * fallback: without a CUDA device every compute entry fails with
+ * MISTRA_KPP_ENODEVICE.
+ */
+#ifndef MISTRA_KPP_H
+#define MISTRA_KPP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { MISTRA_KPP_GAS = 0, MISTRA_KPP_AER = 1, MISTRA_KPP_TOT = 2 };
+
+enum {
+  MISTRA_KPP_OK = 0,
+  MISTRA_KPP_EINVAL = -1,    /* bad mechanism id / null pointer / negative size        */
+  MISTRA_KPP_EOPTS = -2,     /* option rejected; same tests as Rosenbrock_x gas.f:950-1051 */
+  MISTRA_KPP_ENODEVICE = -3, /* no usable CUDA device                                   */
+  MISTRA_KPP_ECUDA = -4,     /* CUDA runtime error (see mistra_kpp_last_error)          */
+  MISTRA_KPP_ENOMEM = -5
+};
+
+/* Integrator options.  Field meaning = RPAR/IPAR of Rosenbrock_x (gas.f:786-870):
+ * a zero selects the reference default.  mistra_kpp_default_opts() fills the
+ * values INTEGRATE_x hard-codes (gas.f:739-746): Ros3, non-autonomous, scalar
+ * tolerances RTOL=1e-3 ATOL=1e-25, Hstart=1e-3; the rest default inside
+ * Rosenbrock_x to Hmin=0, Hmax=|t1-t0|, FacMin=.2, FacMax=6, FacRej=.1,
+ * FacSafe=.9, 100000 steps. */
+typedef struct mistra_kpp_opts {
+  double rtol, atol;                      /* RTOL(1), ATOL(1)  (IPAR(2)=1: scalar) */
+  double hmin, hmax, hstart;              /* RPAR(1..3) */
+  double facmin, facmax, facrej, facsafe; /* RPAR(4..7) */
+  int32_t max_steps;                      /* IPAR(3) */
+  int32_t autonomous;                     /* IPAR(1)!=0; only changes the Nfun statistic */
+  int32_t f32_literals;                   /* 1 (default): non-integer stoichiometric literals
+                                             are binary32 as under the reference's preferred
+                                             compiler flags; 0: binary64 (-r8 build) */
+  int32_t reserved;
+} mistra_kpp_opts;
+
+void mistra_kpp_default_opts(mistra_kpp_opts *o);
+
+/* Sizes of a mechanism (gas_Parameters.h:26-49 and the aer_/tot_ twins). */
+int mistra_kpp_query(int mech, int *nvar, int *nfix, int *nreact, int *lu_nonzero);
+
+/* SPC_NAMES(i+1) of the mechanism (gas.f:6867-6891), i in [0, NVAR+NFIX); NULL if out of
+ * range.  mk_interface (utils.f90:84-140) matches species by these names. */
+const char *mistra_kpp_spc_name(int mech, int i);
+
+/* Per-cell exit codes written to ierr[] - those of ros_ErrorMsg_x (gas.f:1474-1509):
+ *   1 success; -6 more than max_steps steps; -7 step size too small;
+ *  -8 matrix repeatedly singular.  As in the reference (gas.f:764-770) a failed cell
+ * returns its partially advanced VAR. */
+
+/* B2 - integrate ncell independent cells of one mechanism from t0 to t1.
+ *   rconst [ncell][NREACT]  RCONST of each cell, frozen over the step (gas.f:1964-1967)
+ *   fix    [ncell][NFIX]    FIX of each cell
+ *   var    [ncell][NVAR]    VAR of each cell, in/out
+ *   ierr   [ncell]          or NULL
+ *   stats  [ncell][8]       Nfun,Njac,Nstp,Nacc,Nrej,Ndec,Nsol,Nsng (gas.f:913-915) or NULL
+ *   hexit  [ncell]          last step size = STEPMIN on return of INTEGRATE_x (gas.f:770) or NULL
+ *   texit  [ncell]          time reached = TIN on return of INTEGRATE_x (gas.f:769) or NULL
+ * Row-major C arrays = Fortran arrays (NREACT,ncell) etc.  HOST buffers; the call
+ * stages them through pinned memory to the current CUDA device, runs, copies the
+ * results back and returns when they are in place.  `stream` is a cudaStream_t
+ * (NULL = the library's own stream). */
+int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const double *fix,
+                         double *var, double t0, double t1, const mistra_kpp_opts *o,
+                         int32_t *ierr, int32_t *stats, double *hexit, double *texit,
+                         void *stream);
+
+/* Same contract with DEVICE buffers on the current device; asynchronous on
+ * `stream` (no host synchronisation).  This is the entry the multi-GPU driver
+ * and the device-resident benchmark use. */
+int mistra_kpp_integrate_device(int mech, int64_t ncell, const double *d_rconst,
+                                const double *d_fix, double *d_var, double t0, double t1,
+                                const mistra_kpp_opts *o, int32_t *d_ierr, int32_t *d_stats,
+                                double *d_hexit, double *d_texit, void *stream);
+
+/* Measured FP64 FMA throughput of the current device in TFLOP/s (an 8-chain DFMA
+ * microbenchmark; FMA = 2 flops) - the denominator of the FP64 roofline, since
+ * MEASURED_PEAKS.json carries no FP64 figure.  Negative on error. */
+double mistra_kpp_fp64_peak_tflops(void);
+
+/* Kernels launched by this library since load (the bench's gpu_launches claim). */
+int64_t mistra_kpp_launch_count(void);
+
+/* Release device workspaces, pinned staging buffers and the library stream. */
+int mistra_kpp_finalize(void);
+
+const char *mistra_kpp_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,144 @@
+"""Build the native pieces in-tree (sm_100a only):
+
+  mistra_b200/libmistra_kpp.so          product library (C-ABI of include/mistra_kpp.h)
+  mistra_b200/libmistra_kpp_strict.so   same sources with -DKPP_STRICT -fmad=false: divisions and
+                                        summation order exactly as the reference; used by the
+                                        bit-parity test only
+
+Sources are generated from mistra_b200/mech/*.json by mechgen.emit_cuda, compiled
+with nvcc (cross-compiles without a GPU) and linked with -cudart shared-free
+static runtime.  Re-running is incremental (content hashes).
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+
+NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+HOSTCXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", HOSTCXX]
+
+UNITS = ["kpp_mech_g.cu", "kpp_mech_a.cu", "kpp_mech_t.cu", "kpp_api.cu", "_gen/kpp_names.cpp"]
+
+
+def _hash(paths, extra):
+    h = hashlib.sha256()
+    h.update(repr(extra).encode())
+    for p in paths:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _deps(unit):
+    deps = [os.path.join(CSRC, unit), os.path.join(CSRC, "kpp_batch.h"),
+            os.path.join(ROOT, "include", "mistra_kpp.h")]
+    if unit.startswith("kpp_mech_"):
+        x = unit[len("kpp_mech_")]
+        deps += [os.path.join(CSRC, "_gen", "mech_%s.cuh" % x), os.path.join(CSRC, "ros3_kernel.inc")]
+    return deps
+
+
+def _compile(unit, flags, tag, verbose):
+    os.makedirs(OBJ, exist_ok=True)
+    obj = os.path.join(OBJ, "%s.%s.o" % (unit.replace("/", "_"), tag))
+    stamp = obj + ".sha"
+    hv = _hash(_deps(unit), (flags, NVCC))
+    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == hv:
+        return obj
+    cmd = [NVCC] + ARCH + COMMON + flags + ["-c", os.path.join(CSRC, unit), "-o", obj]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s" % (unit, r.stdout))
+    if verbose and r.stdout.strip():
+        print(r.stdout)
+    with open(stamp, "w") as f:
+        f.write(hv)
+    return obj
+
+
+def build(verbose=False, strict=True, ptxas_v=False):
+    subprocess.check_call([sys.executable, "-m", "mistra_b200.mechgen.emit_cuda"], cwd=ROOT,
+                          stdout=subprocess.DEVNULL)
+    variants = [("fast", [], "libmistra_kpp.so")]
+    if strict:
+        variants.append(("strict", ["-DKPP_STRICT", "-fmad=false"], "libmistra_kpp_strict.so"))
+    jobs = []
+    with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
+        for tag, flags, _ in variants:
+            fl = flags + (["-Xptxas", "-v"] if ptxas_v else [])
+            for u in UNITS:
+                jobs.append((tag, ex.submit(_compile, u, fl, tag, verbose)))
+        objs = {}
+        for tag, j in jobs:
+            objs.setdefault(tag, []).append(j.result())
+    outs = []
+    for tag, flags, soname in variants:
+        so = os.path.join(HERE, soname)
+        newest = max(os.path.getmtime(o) for o in objs[tag])
+        if not os.path.exists(so) or os.path.getmtime(so) < newest:
+            cmd = [NVCC] + ARCH + ["-shared", "-ccbin", HOSTCXX, "-cudart", "static", "-o", so] + objs[tag]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+        outs.append(so)
+    outs.append(build_rconst(verbose))
+    outs.append(build_f77(verbose))
+    return outs
+
+
+def build_f77(verbose=False):
+    """Boundary B1 shims (include/mistra_kpp_f77.h) over libmistra_kpp.so."""
+    so = os.path.join(HERE, "libmistra_kpp_f77.so")
+    src = os.path.join(CSRC, "f77_shim.c")
+    deps = [src, os.path.join(ROOT, "include", "mistra_kpp_f77.h"), os.path.join(ROOT, "include", "mistra_kpp.h")]
+    hv = _hash(deps, HOSTCXX)
+    stamp = os.path.join(OBJ, "f77.sha")
+    if os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == hv:
+        return so
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    cmd = [cc, "-O2", "-fPIC", "-shared", "-o", so, src, "-L" + HERE, "-lmistra_kpp",
+           "-Wl,-rpath,$ORIGIN"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    with open(stamp, "w") as f:
+        f.write(hv)
+    return so
+
+
+def build_rconst(verbose=False):
+    """Host-side Update_RCONST_x producer (include/mistra_rconst.h), plain g++."""
+    so = os.path.join(HERE, "libmistra_rconst.so")
+    srcs = [os.path.join(CSRC, "rconst_host.cpp"), os.path.join(CSRC, "_gen", "kpp_names.cpp")]
+    deps = srcs + [os.path.join(CSRC, "rate_laws.h"), os.path.join(ROOT, "include", "mistra_rconst.h")] + [
+        os.path.join(CSRC, "_gen", "rconst_%s.inc" % x) for x in "gat"]
+    hv = _hash(deps, HOSTCXX)
+    stamp = os.path.join(OBJ, "rconst.sha")
+    os.makedirs(OBJ, exist_ok=True)
+    if os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == hv:
+        return so
+    cmd = [HOSTCXX, "-O2", "-fPIC", "-fopenmp", "-ffp-contract=off", "-shared", "-o", so] + srcs
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    with open(stamp, "w") as f:
+        f.write(hv)
+    return so
+
+
+if __name__ == "__main__":
+    print("\n".join(build(verbose=True, strict="--no-strict" not in sys.argv,
+                          ptxas_v="--ptxas-v" in sys.argv)))

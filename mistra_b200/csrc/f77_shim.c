@@ -1,0 +1,55 @@
+/* Boundary B1 (include/mistra_kpp_f77.h): per-cell replacements of
+ * INTEGRATE_g/_a/_t (/root/reference/src/gas.f:710-773, aer.f:1408, tot.f:2812)
+ * over the batched C ABI.  The COMMON blocks are referenced weakly so that the
+ * library also loads into a process that has no Fortran host (tests). */
+#include "../../include/mistra_kpp_f77.h"
+#include "../../include/mistra_kpp.h"
+
+#include <stdio.h>
+
+extern struct mistra_gdata_g gdata_g_ __attribute__((weak));
+extern struct mistra_gdata_a gdata_a_ __attribute__((weak));
+extern struct mistra_gdata_t gdata_t_ __attribute__((weak));
+
+static void integrate_common(int mech, int nvar, double *C, double *RCONST, double *ATOL,
+                             double *RTOL, double *STEPMIN, double *tin, double *tout)
+{
+  mistra_kpp_opts o;
+  int32_t ierr = 0;
+  double hexit = 0.0, texit = *tin;
+  int i, rc;
+  mistra_kpp_default_opts(&o);         /* IPAR(1)=0, IPAR(2)=1, IPAR(4)=2, RPAR(3)=1d-3 */
+  for (i = 0; i < nvar; i++) {         /* gas.f:745-746 */
+    RTOL[i] = 1.0e-3;
+    ATOL[i] = 1.0e-25;
+  }
+  rc = mistra_kpp_integrate(mech, 1, RCONST, C + nvar, C, *tin, *tout, &o, &ierr, 0, &hexit,
+                            &texit, 0);
+  if (rc != 0) {
+    fprintf(stderr, " mistra_kpp: %s\n", mistra_kpp_last_error());
+    return;
+  }
+  if (ierr < 0)                         /* gas.f:764-767 */
+    fprintf(stderr, " Rosenbrock: Unsucessful step at T=%g (IERR=%d)\n", *tin, (int)ierr);
+  *tin = texit;                         /* gas.f:769 */
+  *STEPMIN = hexit;                     /* gas.f:770 */
+}
+
+void integrate_g_(double *tin, double *tout)
+{
+  struct mistra_gdata_g *g = &gdata_g_;
+  if (!g) { fprintf(stderr, " mistra_kpp: COMMON /GDATA_g/ not linked\n"); return; }
+  integrate_common(MISTRA_KPP_GAS, 102, g->C, g->RCONST, g->ATOL, g->RTOL, &g->STEPMIN, tin, tout);
+}
+void integrate_a_(double *tin, double *tout)
+{
+  struct mistra_gdata_a *g = &gdata_a_;
+  if (!g) { fprintf(stderr, " mistra_kpp: COMMON /GDATA_a/ not linked\n"); return; }
+  integrate_common(MISTRA_KPP_AER, 257, g->C, g->RCONST, g->ATOL, g->RTOL, &g->STEPMIN, tin, tout);
+}
+void integrate_t_(double *tin, double *tout)
+{
+  struct mistra_gdata_t *g = &gdata_t_;
+  if (!g) { fprintf(stderr, " mistra_kpp: COMMON /GDATA_t/ not linked\n"); return; }
+  integrate_common(MISTRA_KPP_TOT, 417, g->C, g->RCONST, g->ATOL, g->RTOL, &g->STEPMIN, tin, tout);
+}

@@ -1,0 +1,380 @@
+// C-ABI layer of libmistra_kpp.so (include/mistra_kpp.h): option decoding as in
+// Rosenbrock_x (/root/reference/src/gas.f:950-1051), device workspaces, host
+// staging and kernel launches.  No CPU fallback: every compute entry needs a
+// CUDA device.
+#include "../../include/mistra_kpp.h"
+#include "kpp_batch.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+namespace {
+
+std::mutex g_mu;
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+struct MechState {
+  double *ws = nullptr;
+  size_t ws_bytes = 0;
+  int blocks = 0;
+  int coef_variant = -1;  // -1 unset, 0 f64 literals, 1 f32 literals
+};
+
+struct DeviceState {
+  bool init = false;
+  int dev = -1;
+  int num_sm = 0;
+  cudaStream_t stream = nullptr;
+  unsigned long long *counter = nullptr;
+  MechState mech[3];
+  // device staging for the host-buffer entry
+  void *d_stage = nullptr;
+  size_t d_stage_bytes = 0;
+  // pinned staging for pageable host buffers
+  void *h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+};
+
+constexpr int kMaxDev = 16;
+DeviceState g_dev[kMaxDev];
+
+int fail(int code, const std::string &msg)
+{
+  g_err = msg;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? MISTRA_KPP_ENODEVICE
+         : (e == cudaErrorMemoryAllocation)                           ? MISTRA_KPP_ENOMEM
+                                                                      : MISTRA_KPP_ECUDA;
+}
+
+#define CK(call)                                          \
+  do {                                                    \
+    cudaError_t e_ = (call);                              \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
+  } while (0)
+
+const KppMechInfo *mech_info(int mech)
+{
+  switch (mech) {
+    case MISTRA_KPP_GAS: return kpp_mech_info_g();
+    case MISTRA_KPP_AER: return kpp_mech_info_a();
+    case MISTRA_KPP_TOT: return kpp_mech_info_t();
+  }
+  return nullptr;
+}
+
+int get_device(DeviceState **out)
+{
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev < 0 || dev >= kMaxDev) return fail(MISTRA_KPP_ENODEVICE, "device index out of range");
+  DeviceState &d = g_dev[dev];
+  if (!d.init) {
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, dev));
+    d.dev = dev;
+    d.num_sm = p.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&d.counter, sizeof(unsigned long long)));
+    d.init = true;
+  }
+  *out = &d;
+  return 0;
+}
+
+// Rosenbrock_x option decoding, gas.f:950-1051 (same tests, same defaults)
+int decode_opts(const mistra_kpp_opts *o, double t0, double t1, KppBatch *b)
+{
+  mistra_kpp_opts dflt;
+  if (!o) { mistra_kpp_default_opts(&dflt); o = &dflt; }
+  const double Roundoff = 2.220446049250313e-16, DeltaMin = 1.0e-5;
+  if (o->max_steps == 0) b->max_steps = 100000;
+  else if (o->max_steps > 0) b->max_steps = o->max_steps;
+  else return fail(MISTRA_KPP_EOPTS, "max_steps < 0 (IPAR(3), ros_ErrorMsg -1)");
+  if (o->hmin == 0.0) b->hmin = 0.0;
+  else if (o->hmin > 0.0) b->hmin = o->hmin;
+  else return fail(MISTRA_KPP_EOPTS, "hmin < 0 (RPAR(1), ros_ErrorMsg -3)");
+  if (o->hmax == 0.0) b->hmax = std::fabs(t1 - t0);
+  else if (o->hmax > 0.0) b->hmax = std::fmin(std::fabs(o->hmax), std::fabs(t1 - t0));
+  else return fail(MISTRA_KPP_EOPTS, "hmax < 0 (RPAR(2), ros_ErrorMsg -3)");
+  if (o->hstart == 0.0) b->hstart = std::fmax(b->hmin, DeltaMin);
+  else if (o->hstart > 0.0) b->hstart = std::fmin(std::fabs(o->hstart), std::fabs(t1 - t0));
+  else return fail(MISTRA_KPP_EOPTS, "hstart < 0 (RPAR(3), ros_ErrorMsg -3)");
+  auto fac = [&](double v, double d, double *out, const char *nm) -> int {
+    if (v == 0.0) *out = d;
+    else if (v > 0.0) *out = v;
+    else return fail(MISTRA_KPP_EOPTS, std::string(nm) + " < 0 (RPAR(4..7), ros_ErrorMsg -4)");
+    return 0;
+  };
+  int rc;
+  if ((rc = fac(o->facmin, 0.2, &b->facmin, "facmin"))) return rc;
+  if ((rc = fac(o->facmax, 6.0, &b->facmax, "facmax"))) return rc;
+  if ((rc = fac(o->facrej, 0.1, &b->facrej, "facrej"))) return rc;
+  if ((rc = fac(o->facsafe, 0.9, &b->facsafe, "facsafe"))) return rc;
+  if (!(o->atol > 0.0) || !(o->rtol > 10.0 * Roundoff) || !(o->rtol < 1.0))
+    return fail(MISTRA_KPP_EOPTS, "unreasonable tolerances (ros_ErrorMsg -5)");
+  b->atol = o->atol;
+  b->rtol = o->rtol;
+  b->autonomous = o->autonomous ? 1 : 0;
+  b->t0 = t0;
+  b->t1 = t1;
+  return 0;
+}
+
+double literal_value(const char *lit, int f32)
+{
+  // Fortran default-REAL literal: binary32 under the reference's preferred flags
+  return f32 ? (double)strtof(lit, nullptr) : strtod(lit, nullptr);
+}
+
+int ensure_mech(DeviceState &d, int mech, const KppMechInfo *mi, int f32, cudaStream_t st)
+{
+  MechState &ms = d.mech[mech];
+  if (!ms.ws) {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mi->kernel, KPP_BLOCK, 0));
+    if (per_sm < 1) return fail(MISTRA_KPP_ECUDA, "kernel does not fit on an SM");
+    if (const char *e = getenv("MISTRA_KPP_BLOCKS_PER_SM")) {
+      int v = atoi(e);
+      if (v >= 1 && v < per_sm) per_sm = v;
+    }
+    ms.blocks = per_sm * d.num_sm;
+    const size_t warps = (size_t)ms.blocks * (KPP_BLOCK / 32);
+    ms.ws_bytes = warps * (size_t)mi->nslot * 32 * sizeof(double);
+    CK(cudaMalloc(&ms.ws, ms.ws_bytes));
+  }
+  if (ms.coef_variant != f32) {
+    double h[64];
+    if (mi->ncoef > 64) return fail(MISTRA_KPP_EINVAL, "coefficient table too large");
+    for (int i = 0; i < mi->ncoef; ++i) h[i] = literal_value(mi->coef_literals[i], f32);
+    CK(mi->set_coef(h, st));
+    CK(cudaStreamSynchronize(st));  // h is on the stack
+    ms.coef_variant = f32;
+  }
+  return 0;
+}
+
+int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rconst,
+                  const double *d_fix, double *d_var, double t0, double t1,
+                  const mistra_kpp_opts *o, int32_t *d_ierr, int32_t *d_stats, double *d_hexit,
+                  double *d_texit, cudaStream_t st)
+{
+  const KppMechInfo *mi = mech_info(mech);
+  KppBatch b;
+  memset(&b, 0, sizeof(b));
+  int rc = decode_opts(o, t0, t1, &b);
+  if (rc) return rc;
+  const int f32 = o ? (o->f32_literals ? 1 : 0) : 1;
+  if ((rc = ensure_mech(d, mech, mi, f32, st))) return rc;
+  if (ncell == 0) return 0;
+  MechState &ms = d.mech[mech];
+  b.rconst = d_rconst;
+  b.fix = d_fix;
+  b.var = d_var;
+  b.ierr = d_ierr;
+  b.stats = d_stats;
+  b.hexit = d_hexit;
+  b.texit = d_texit;
+  b.ncell = ncell;
+  b.ws = ms.ws;
+  b.counter = d.counter;
+  CK(cudaMemsetAsync(d.counter, 0, sizeof(unsigned long long), st));
+  long long need_blocks = (ncell + KPP_BLOCK - 1) / KPP_BLOCK;
+  int blocks = (int)(need_blocks < ms.blocks ? need_blocks : ms.blocks);
+  CK(mi->launch(b, blocks, st));
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+// FP64 FMA throughput probe: 8 independent DFMA chains per thread, every lane busy.
+// This is the measured denominator of the FP64 roofline (MEASURED_PEAKS.json has
+// no FP64 entry); it is not part of the chemistry path.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 12345.678) out[0] = s;  // never true: keeps the chains alive
+}
+
+}  // namespace
+
+extern "C" {
+
+// Measured FP64 FMA peak of the current device in TFLOP/s (FMA = 2 flops); < 0 on error.
+double mistra_kpp_fp64_peak_tflops(void)
+{
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceState *d;
+  if (get_device(&d)) return -1.0;
+  double *out = nullptr;
+  if (cudaMalloc(&out, 8) != cudaSuccess) return -1.0;
+  const int blocks = d->num_sm * 8, iters = 1 << 15;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = -1.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, d->stream);
+    fp64_peak_kernel<<<blocks, 256, 0, d->stream>>>(out, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1, d->stream);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 8.0 * (double)iters * 256.0 * blocks / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}
+
+void mistra_kpp_default_opts(mistra_kpp_opts *o)
+{
+  memset(o, 0, sizeof(*o));
+  o->rtol = 1.0e-3;    // gas.f:745
+  o->atol = 1.0e-25;   // gas.f:746
+  o->hstart = 1.0e-3;  // gas.f:743
+  o->f32_literals = 1;
+}
+
+int mistra_kpp_query(int mech, int *nvar, int *nfix, int *nreact, int *lu_nonzero)
+{
+  const KppMechInfo *mi = mech_info(mech);
+  if (!mi) return fail(MISTRA_KPP_EINVAL, "unknown mechanism id");
+  if (nvar) *nvar = mi->nvar;
+  if (nfix) *nfix = mi->nfix;
+  if (nreact) *nreact = mi->nreact;
+  if (lu_nonzero) *lu_nonzero = mi->lu_nonzero;
+  return 0;
+}
+
+const char *mistra_kpp_spc_name_impl(int mech, int i);  // kpp_names.cpp (generated table)
+
+const char *mistra_kpp_spc_name(int mech, int i) { return mistra_kpp_spc_name_impl(mech, i); }
+
+int mistra_kpp_integrate_device(int mech, int64_t ncell, const double *d_rconst,
+                                const double *d_fix, double *d_var, double t0, double t1,
+                                const mistra_kpp_opts *o, int32_t *d_ierr, int32_t *d_stats,
+                                double *d_hexit, double *d_texit, void *stream)
+{
+  if (!mech_info(mech)) return fail(MISTRA_KPP_EINVAL, "unknown mechanism id");
+  if (ncell < 0) return fail(MISTRA_KPP_EINVAL, "ncell < 0");
+  if (ncell > 0 && (!d_rconst || !d_fix || !d_var))
+    return fail(MISTRA_KPP_EINVAL, "null rconst/fix/var");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceState *d;
+  int rc = get_device(&d);
+  if (rc) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+  return launch_device(*d, mech, ncell, d_rconst, d_fix, d_var, t0, t1, o, d_ierr, d_stats,
+                       d_hexit, d_texit, st);
+}
+
+int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const double *fix,
+                         double *var, double t0, double t1, const mistra_kpp_opts *o,
+                         int32_t *ierr, int32_t *stats, double *hexit, double *texit,
+                         void *stream)
+{
+  const KppMechInfo *mi = mech_info(mech);
+  if (!mi) return fail(MISTRA_KPP_EINVAL, "unknown mechanism id");
+  if (ncell < 0) return fail(MISTRA_KPP_EINVAL, "ncell < 0");
+  if (ncell > 0 && (!rconst || !fix || !var)) return fail(MISTRA_KPP_EINVAL, "null rconst/fix/var");
+  {
+    KppBatch tmp;
+    int rc = decode_opts(o, t0, t1, &tmp);  // reject bad options before touching the device
+    if (rc) return rc;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceState *d;
+  int rc = get_device(&d);
+  if (rc) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+  if (ncell == 0) return 0;
+
+  // device staging: [rconst | fix | var | hexit | texit | ierr | stats], 256 B aligned sections
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t n = (size_t)ncell;
+  const size_t b_rc = al(n * mi->nreact * 8), b_fx = al(n * mi->nfix * 8), b_vr = al(n * mi->nvar * 8);
+  const size_t b_hx = al(n * 8), b_ie = al(n * 4), b_st = al(n * 32);
+  const size_t total = b_rc + b_fx + b_vr + 2 * b_hx + b_ie + b_st;
+  if (d->d_stage_bytes < total) {
+    if (d->d_stage) cudaFree(d->d_stage);
+    d->d_stage = nullptr;
+    d->d_stage_bytes = 0;
+    CK(cudaMalloc(&d->d_stage, total));
+    d->d_stage_bytes = total;
+  }
+  char *p = (char *)d->d_stage;
+  double *d_rc = (double *)p; p += b_rc;
+  double *d_fx = (double *)p; p += b_fx;
+  double *d_vr = (double *)p; p += b_vr;
+  double *d_hx = (double *)p; p += b_hx;
+  double *d_tx = (double *)p; p += b_hx;
+  int32_t *d_ie = (int32_t *)p; p += b_ie;
+  int32_t *d_st = (int32_t *)p;
+
+  // Host buffers may be pageable (Fortran arrays) or pinned; cudaMemcpyAsync
+  // handles both (pinned ones overlap with the kernel of a previous call).
+  CK(cudaMemcpyAsync(d_rc, rconst, n * mi->nreact * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_fx, fix, n * mi->nfix * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_vr, var, n * mi->nvar * 8, cudaMemcpyHostToDevice, st));
+  rc = launch_device(*d, mech, ncell, d_rc, d_fx, d_vr, t0, t1, o, ierr ? d_ie : nullptr,
+                     stats ? d_st : nullptr, hexit ? d_hx : nullptr, texit ? d_tx : nullptr, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(var, d_vr, n * mi->nvar * 8, cudaMemcpyDeviceToHost, st));
+  if (ierr) CK(cudaMemcpyAsync(ierr, d_ie, n * 4, cudaMemcpyDeviceToHost, st));
+  if (stats) CK(cudaMemcpyAsync(stats, d_st, n * 32, cudaMemcpyDeviceToHost, st));
+  if (hexit) CK(cudaMemcpyAsync(hexit, d_hx, n * 8, cudaMemcpyDeviceToHost, st));
+  if (texit) CK(cudaMemcpyAsync(texit, d_tx, n * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int64_t mistra_kpp_launch_count(void) { return g_launches.load(); }
+
+int mistra_kpp_finalize(void)
+{
+  std::lock_guard<std::mutex> lk(g_mu);
+  int cur = -1;
+  cudaGetDevice(&cur);
+  for (int i = 0; i < kMaxDev; ++i) {
+    DeviceState &d = g_dev[i];
+    if (!d.init) continue;
+    cudaSetDevice(i);
+    cudaDeviceSynchronize();
+    for (auto &m : d.mech) {
+      if (m.ws) cudaFree(m.ws);
+      m = MechState();
+    }
+    if (d.counter) cudaFree(d.counter);
+    if (d.d_stage) cudaFree(d.d_stage);
+    if (d.h_stage) cudaFreeHost(d.h_stage);
+    if (d.stream) cudaStreamDestroy(d.stream);
+    d = DeviceState();
+  }
+  if (cur >= 0) cudaSetDevice(cur);
+  return 0;
+}
+
+const char *mistra_kpp_last_error(void) { return g_err.c_str(); }
+
+}  // extern "C"

@@ -1,0 +1,22 @@
+// Mechanism 'a' device code: generated straight-line Fun/Jac/LU/solve + the Ros3 kernel.
+#include "kpp_batch.h"
+#include "_gen/mech_a.cuh"
+#define MECH_NS mech_a
+#define ROS3_KERNEL ros3_kernel_a
+#define ROS3_LAUNCH ros3_launch_a
+#include "ros3_kernel.inc"
+
+namespace mech_a {
+static cudaError_t set_coef(const double *h, cudaStream_t st)
+{
+  return cudaMemcpyToSymbolAsync(c_coef, h, sizeof(double) * NCOEF, 0, cudaMemcpyHostToDevice, st);
+}
+}  // namespace mech_a
+
+const KppMechInfo *kpp_mech_info_a()
+{
+  using namespace mech_a;
+  static const KppMechInfo info = {NVAR, NFIX, NREACT, LU_NONZERO, NSLOT, NCOEF, coef_literals,
+                                   (const void *)ros3_kernel_a, ros3_launch_a, set_coef};
+  return &info;
+}

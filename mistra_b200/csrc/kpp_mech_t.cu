@@ -1,0 +1,22 @@
+// Mechanism 't' device code: generated straight-line Fun/Jac/LU/solve + the Ros3 kernel.
+#include "kpp_batch.h"
+#include "_gen/mech_t.cuh"
+#define MECH_NS mech_t
+#define ROS3_KERNEL ros3_kernel_t
+#define ROS3_LAUNCH ros3_launch_t
+#include "ros3_kernel.inc"
+
+namespace mech_t {
+static cudaError_t set_coef(const double *h, cudaStream_t st)
+{
+  return cudaMemcpyToSymbolAsync(c_coef, h, sizeof(double) * NCOEF, 0, cudaMemcpyHostToDevice, st);
+}
+}  // namespace mech_t
+
+const KppMechInfo *kpp_mech_info_t()
+{
+  using namespace mech_t;
+  static const KppMechInfo info = {NVAR, NFIX, NREACT, LU_NONZERO, NSLOT, NCOEF, coef_literals,
+                                   (const void *)ros3_kernel_t, ros3_launch_t, set_coef};
+  return &info;
+}

@@ -1,0 +1,160 @@
+"""Host-side mirror of the reference's KPP driver interface over the C ABI
+(include/mistra_kpp.h, libmistra_kpp.so).
+
+Names follow the reference: `integrate` is INTEGRATE_x(TIN,TOUT) for a batch of
+cells (/root/reference/src/gas.f:710, aer.f:1408, tot.f:2812); `MECH_*` are the
+three KPP mechanisms kpp_driver dispatches to (kpp.f90:4451-4468); the error codes
+are those of ros_ErrorMsg_x (gas.f:1474-1509).
+
+There is no CPU implementation behind this module: if the CUDA library is missing
+or no device is present, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+MECH_GAS, MECH_AER, MECH_TOT = 0, 1, 2
+MECH_NAMES = ("gas", "aer", "tot")
+STAT_NAMES = ("Nfun", "Njac", "Nstp", "Nacc", "Nrej", "Ndec", "Nsol", "Nsng")
+
+
+class KppError(RuntimeError):
+    pass
+
+
+class KppOpts(C.Structure):
+    """RPAR/IPAR of Rosenbrock_x (gas.f:786-870); zero selects the reference default."""
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double),
+                ("hmin", C.c_double), ("hmax", C.c_double), ("hstart", C.c_double),
+                ("facmin", C.c_double), ("facmax", C.c_double), ("facrej", C.c_double),
+                ("facsafe", C.c_double),
+                ("max_steps", C.c_int32), ("autonomous", C.c_int32),
+                ("f32_literals", C.c_int32), ("reserved", C.c_int32)]
+
+
+_LIBS = {}
+
+
+def library(strict=False):
+    """Load libmistra_kpp.so (or the -DKPP_STRICT -fmad=false test build)."""
+    name = "libmistra_kpp_strict.so" if strict else "libmistra_kpp.so"
+    if name not in _LIBS:
+        so = os.path.join(_HERE, name)
+        if not os.path.exists(so):
+            raise KppError("%s is missing: build it with `python -m mistra_b200.build` "
+                           "(there is no CPU fallback)" % so)
+        L = C.CDLL(so)
+        dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p
+        L.mistra_kpp_default_opts.argtypes = [C.POINTER(KppOpts)]
+        L.mistra_kpp_default_opts.restype = None
+        L.mistra_kpp_query.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 4
+        L.mistra_kpp_spc_name.argtypes = [C.c_int, C.c_int]
+        L.mistra_kpp_spc_name.restype = C.c_char_p
+        L.mistra_kpp_integrate.argtypes = [C.c_int, C.c_int64, dp, dp, dp, C.c_double, C.c_double,
+                                           C.POINTER(KppOpts), ip, ip, dp, dp, vp]
+        L.mistra_kpp_integrate_device.argtypes = [C.c_int, C.c_int64, vp, vp, vp, C.c_double,
+                                                  C.c_double, C.POINTER(KppOpts), vp, vp, vp, vp, vp]
+        L.mistra_kpp_launch_count.restype = C.c_int64
+        L.mistra_kpp_fp64_peak_tflops.restype = C.c_double
+        L.mistra_kpp_last_error.restype = C.c_char_p
+        _LIBS[name] = L
+    return _LIBS[name]
+
+
+def _check(L, rc):
+    if rc != 0:
+        raise KppError("mistra_kpp error %d: %s" % (rc, (L.mistra_kpp_last_error() or b"").decode()))
+
+
+def default_opts(strict=False, **kw):
+    o = KppOpts()
+    library(strict).mistra_kpp_default_opts(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def query(mech, strict=False):
+    """(NVAR, NFIX, NREACT, LU_NONZERO) of a mechanism (*_Parameters.h)."""
+    L = library(strict)
+    v = [C.c_int() for _ in range(4)]
+    _check(L, L.mistra_kpp_query(mech, *[C.byref(x) for x in v]))
+    return tuple(x.value for x in v)
+
+
+def spc_name(mech, i, strict=False):
+    s = library(strict).mistra_kpp_spc_name(mech, i)
+    return s.decode() if s else None
+
+
+def integrate(mech, rconst, fix, var, t0=0.0, t1=10.0, opts=None, strict=False, out=None):
+    """INTEGRATE_x for a batch of cells held in HOST numpy arrays.
+
+    rconst [ncell,NREACT], fix [ncell,NFIX], var [ncell,NVAR] (not modified).
+    Returns (var_out, ierr[ncell], stats[ncell,8], hexit[ncell], texit[ncell])."""
+    L = library(strict)
+    nvar, nfix, nreact, _ = query(mech, strict)
+    var_in = np.ascontiguousarray(var, dtype=np.float64).reshape(-1, nvar)
+    ncell = var_in.shape[0]
+    var_out = out if out is not None else np.empty_like(var_in)
+    if var_out is not var_in:
+        np.copyto(var_out, var_in)
+    rconst = np.ascontiguousarray(rconst, dtype=np.float64).reshape(ncell, nreact)
+    fix = np.ascontiguousarray(fix, dtype=np.float64).reshape(ncell, nfix)
+    ierr = np.zeros(ncell, dtype=np.int32)
+    stats = np.zeros((ncell, 8), dtype=np.int32)
+    hexit = np.zeros(ncell, dtype=np.float64)
+    texit = np.zeros(ncell, dtype=np.float64)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    o = opts if opts is not None else default_opts(strict)
+    rc = L.mistra_kpp_integrate(mech, ncell, rconst.ctypes.data_as(dp), fix.ctypes.data_as(dp),
+                                var_out.ctypes.data_as(dp), t0, t1, C.byref(o),
+                                ierr.ctypes.data_as(ip), stats.ctypes.data_as(ip),
+                                hexit.ctypes.data_as(dp), texit.ctypes.data_as(dp), None)
+    _check(L, rc)
+    return var_out, ierr, stats, hexit, texit
+
+
+def integrate_device(mech, rconst, fix, var, t0=0.0, t1=10.0, opts=None, ierr=None, stats=None,
+                     hexit=None, texit=None, stream=None, strict=False):
+    """Same contract on DEVICE buffers: torch CUDA tensors (float64 / int32,
+    contiguous) on the current device; `var` is advanced in place.  Asynchronous
+    on `stream` (default: torch's current stream)."""
+    import torch
+    L = library(strict)
+    nvar, nfix, nreact, _ = query(mech, strict)
+    ncell = var.shape[0]
+    for t, w, dt in ((rconst, nreact, torch.float64), (fix, nfix, torch.float64), (var, nvar, torch.float64)):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == dt and tuple(t.shape) == (ncell, w)):
+            raise KppError("integrate_device: bad tensor (need contiguous CUDA %s [%d,%d])" % (dt, ncell, w))
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    o = opts if opts is not None else default_opts(strict)
+
+    def ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+    rc = L.mistra_kpp_integrate_device(mech, ncell, ptr(rconst), ptr(fix), ptr(var), t0, t1,
+                                       C.byref(o), ptr(ierr), ptr(stats), ptr(hexit), ptr(texit),
+                                       C.c_void_p(stream))
+    _check(L, rc)
+
+
+def launch_count(strict=False):
+    return int(library(strict).mistra_kpp_launch_count())
+
+
+def fp64_peak_tflops():
+    """Measured FP64 FMA peak of the current device (TFLOP/s)."""
+    v = library().mistra_kpp_fp64_peak_tflops()
+    if v <= 0:
+        raise KppError("FP64 peak probe failed: no CUDA device?")
+    return v
+
+
+def finalize(strict=False):
+    library(strict).mistra_kpp_finalize()

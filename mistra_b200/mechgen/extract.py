@@ -17,7 +17,7 @@ compact description of each mechanism (``mistra_b200/mech/<name>.json``):
 
 The JSON tables are mechanism *data* (which reaction consumes which species
 with which stoichiometric number); every line of C and CUDA in this repository
-is generated from them by ``emit_oracle.py`` / ``emit_cuda.py`` or written by
+is generated from them by the oracle emitter / ``emit_cuda.py`` or written by
 hand.  The reference tree is needed only to (re)run this script; the committed
 tables make the repository buildable where ``/root/reference`` is absent (the
 GPU box).
