@@ -94,7 +94,8 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
                          void *stream);
 
 /* Same contract with DEVICE buffers on the current device; asynchronous on
- * `stream` (no host synchronisation).  This is the entry the multi-GPU driver
+ * `stream` (a cudaStream_t; NULL = the legacy default stream, as in the CUDA
+ * runtime), no host synchronisation.  This is the entry the multi-GPU driver
  * and the device-resident benchmark use. */
 int mistra_kpp_integrate_device(int mech, int64_t ncell, const double *d_rconst,
                                 const double *d_fix, double *d_var, double t0, double t1,

@@ -284,7 +284,7 @@ int mistra_kpp_integrate_device(int mech, int64_t ncell, const double *d_rconst,
   DeviceState *d;
   int rc = get_device(&d);
   if (rc) return rc;
-  cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream, as in the CUDA runtime
   return launch_device(*d, mech, ncell, d_rconst, d_fix, d_var, t0, t1, o, d_ierr, d_stats,
                        d_hexit, d_texit, st);
 }

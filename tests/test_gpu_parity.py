@@ -22,6 +22,11 @@ MECHS = list(enumerate(mechmod.MECH_NAMES))
 
 def compare(out, ref, stats, stats_o, ierr, ierr_o, hexit, hexit_o, locked_tol=1e-9):
     assert np.array_equal(ierr, ierr_o)
+    # failed cells (ierr < 0) return a partially advanced VAR (gas.f:764-770); they are
+    # counted, not compared (SURVEY 8a trap 9: their path runs through non-finite norms)
+    ok = ierr == 1
+    assert ok.mean() >= 0.9
+    out, ref, stats, stats_o, hexit, hexit_o = out[ok], ref[ok], stats[ok], stats_o[ok], hexit[ok], hexit_o[ok]
     rel = util.rel_err(out, ref)
     assert rel.max() <= util.RTOL, "max rel err %.3e" % rel.max()
     locked = (stats[:, 2:5] == stats_o[:, 2:5]).all(axis=1)
