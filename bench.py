@@ -45,9 +45,9 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cols", type=int, default=int(os.environ.get("MISTRA_BENCH_COLS", "10000")),
                     help="columns per GPU (148 cells each)")
-    ap.add_argument("--mechs", default=os.environ.get("MISTRA_BENCH_MECHS", "gas"))
+    ap.add_argument("--mechs", default=os.environ.get("MISTRA_BENCH_MECHS", "gas,aer"))
     ap.add_argument("--spinup", type=int, default=int(os.environ.get("MISTRA_BENCH_SPINUP", "12")))
-    ap.add_argument("--cpu-sample-cols", type=int, default=2000,
+    ap.add_argument("--cpu-sample-cols", type=int, default=200,
                     help="columns per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -116,31 +116,40 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------
-def build_ensemble(mech, cols, rank, spinup, use_gpu):
+def build_ensemble(mech, cols, rank, spinup, use_gpu, chunk_cols=500):
     """Synthetic per-rank ensemble, spun up so that the timed step sees a stiff
-    quasi-steady radical state.  Spin-up uses the CUDA path when a GPU is present
-    (it is input preparation, not part of the timed region)."""
+    quasi-steady radical state.  Built in chunks of columns (the per-species input
+    arrays of the aqueous mechanism are large).  Spin-up uses the CUDA path when a
+    GPU is present (it is input preparation, not part of the timed region)."""
     from mistra_b200 import synthetic
-    if mech != "gas":
+    cls = {"gas": synthetic.GasEnsemble, "aer": synthetic.AerEnsemble}.get(mech)
+    if cls is None:
         raise SystemExit("bench: synthetic inputs for mechanism %r are not available yet" % mech)
-    ens = synthetic.GasEnsemble(cols, col0=rank * cols)
-    var = ens.var
-    rc = ens.rconst(var)
-    if spinup > 0:
-        if use_gpu:
-            from mistra_b200 import kpp
-            for s in range(spinup):
-                if s and s % 6 == 0:
-                    rc = ens.rconst(var)
-                var, ierr, _, _, _ = kpp.integrate(MECH_ID[mech], rc, ens.fix, var)
-        else:
-            from oracle import kpp_oracle as ko
-            for s in range(spinup):
-                if s and s % 6 == 0:
-                    rc = ens.rconst(var)
-                var = ko.integrate(MECH_ID[mech], rc, ens.fix, var, nthreads=os.cpu_count() or 1)[0]
+    if use_gpu:
+        from mistra_b200 import kpp
+
+        def step(rc, fix, var):
+            return kpp.integrate(MECH_ID[mech], rc, fix, var)[0]
+    else:
+        from oracle import kpp_oracle as ko
+
+        def step(rc, fix, var):
+            return ko.integrate(MECH_ID[mech], rc, fix, var, nthreads=os.cpu_count() or 1)[0]
+    vs, rs, fs = [], [], []
+    for c0 in range(0, cols, chunk_cols):
+        nc = min(chunk_cols, cols - c0)
+        ens = cls(nc, col0=rank * cols + c0)
+        var = ens.var
         rc = ens.rconst(var)
-    return ens, np.ascontiguousarray(var), np.ascontiguousarray(rc), np.ascontiguousarray(ens.fix)
+        for s in range(spinup):
+            if s and s % 6 == 0:
+                rc = ens.rconst(var)
+            var = np.maximum(step(rc, ens.fix, var), 0.0)   # kpp_driver clips negatives (kpp.f90:4473-4477)
+        if spinup > 0:
+            rc = ens.rconst(var)
+        vs.append(var); rs.append(rc); fs.append(ens.fix)
+    return None, np.ascontiguousarray(np.concatenate(vs)), np.ascontiguousarray(np.concatenate(rs)), \
+        np.ascontiguousarray(np.concatenate(fs))
 
 
 def cpu_baseline(mech, var, rc, fix, ncells, threads):
@@ -154,6 +163,18 @@ def cpu_baseline(mech, var, rc, fix, ncells, threads):
     return n / dt, dt, stats
 
 
+def cpu_mixed(batches, frac, threads):
+    """The same mechanism mix as the GPU step: the first `frac` of every batch.
+    Returns (cells, seconds)."""
+    cells, secs = 0, 0.0
+    for mname, var, rc, fix in batches:
+        n = max(1, int(var.shape[0] * frac))
+        _, dt, _ = cpu_baseline(mname, var, rc, fix, n, threads)
+        cells += n
+        secs += dt
+    return cells, secs
+
+
 # ----------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path, i.e.
@@ -163,24 +184,28 @@ def run_reference(args):
     if rank != 0:
         return
     threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    mech = args.mechs.split(",")[0]
+    mechs = args.mechs.split(",")
     cols = args.cpu_sample_cols
-    ens, var, rc, fix = build_ensemble(mech, cols, 0, min(args.spinup, 4), use_gpu=False)
-    n = var.shape[0]
+    batches = []
+    for mname in mechs:
+        _, var, rc, fix = build_ensemble(mname, cols, 0, args.spinup, use_gpu=False, chunk_cols=50)
+        batches.append((mname, var, rc, fix))
+    n = sum(b[1].shape[0] for b in batches)
     for _ in range(args.warmup):
-        cpu_baseline(mech, var, rc, fix, n, threads)
+        cpu_mixed(batches, 1.0, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        rate, dt, stats = cpu_baseline(mech, var, rc, fix, n, threads)
+        cpu_mixed(batches, 1.0, threads)
     dt = (time.perf_counter() - t0) / args.steps
     value = n / dt
+    mech = "+".join(mechs)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "synthetic Mistra ensemble, %s mechanism, Ros3 0->10 s" % mech,
-                   "sample": "%d columns x 148 cells = %d cells per step" % (cols, n)},
+                   "sample": "%d columns = %d cells per step, same gas:aer mix as the b200 arm" % (cols, n)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d cells (%d columns), OpenMP over cells" % (n, cols)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -344,18 +369,18 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        mname, var, rc, fix = batches[0]
-        cpu_baseline(mname, var, rc, fix, 2048, threads)           # warm-up
-        # bounded sample: ~10-20 s of CPU work on all host threads (cells are independent,
-        # so the rate scales linearly to the full batch)
-        r_probe, dt_probe, _ = cpu_baseline(mname, var, rc, fix, min(var.shape[0], 148 * 64), threads)
-        n_all = int(min(var.shape[0], max(148 * 64, r_probe * 12.0)))
-        r_all, dt_all, _ = cpu_baseline(mname, var, rc, fix, n_all, threads)
-        n_1 = int(min(var.shape[0], max(148, r_probe / threads * 4.0)))
-        r_1, dt_1, _ = cpu_baseline(mname, var, rc, fix, n_1, 1)
-        cpu = {"value": r_all, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d %s cells of the same batch, OpenMP over cells, %.1f s" % (n_all, mname, dt_all),
-               "value_1thread": r_1, "sample_1thread": "%d cells, %.1f s" % (n_1, dt_1),
+        cpu_mixed(batches, 2048.0 / ncell_rank, threads)            # warm-up
+        # bounded sample with the same mechanism mix: ~12 s of CPU work on all host threads
+        # (cells are independent, so the rate scales linearly to the full batch)
+        c_probe, t_probe = cpu_mixed(batches, min(1.0, 20000.0 / ncell_rank), threads)
+        frac = min(1.0, 12.0 * (c_probe / t_probe) / ncell_rank)
+        c_all, t_all = cpu_mixed(batches, frac, threads)
+        frac1 = min(1.0, 4.0 * (c_probe / t_probe) / threads / ncell_rank)
+        c_1, t_1 = cpu_mixed(batches, frac1, 1)
+        cpu = {"value": c_all / t_all, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "first %.3g of every batch (%d cells, mechanisms %s), OpenMP over cells, %.1f s"
+                         % (frac, c_all, "+".join(mechs), t_all),
+               "value_1thread": c_1 / t_1, "sample_1thread": "%d cells, %.1f s" % (c_1, t_1),
                "note": "C restatement of the reference Fortran (no Fortran compiler in the image)"}
 
     if rank == 0:
@@ -365,7 +390,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "synthetic ensemble of independent Mistra columns (SURVEY 8d), "
-                                   "%d columns x 148 cells per GPU, mechanisms: %s; Ros3 0->10 s, "
+                                   "%d columns per GPU (148 gas cells + 98 aer cells each), mechanisms: %s; Ros3 0->10 s, "
                                    "RTOL 1e-3 ATOL 1e-25 Hstart 1e-3" % (args.cols, "+".join(mechs)),
                        "cells_per_gpu": ncell_rank, "columns_per_gpu": args.cols,
                        "parallelism": "cells sharded by column over %d GPU(s), no data-path collective" % world,

@@ -179,3 +179,181 @@ class GasEnsemble:
         return rc.update_rconst(0, self.cb1[sl], self.scal[sl], self.ph_rat[sl], c,
                                 yhenry=self.yhenry[sl], yxkmtd=self.yxkmtd[sl], yxeq=self.yxeq[sl],
                                 ycwd=self.ycwd[sl], f32_literals=self.f32)
+
+
+# ---------------------------------------------------------------------------------
+# Aqueous-phase inputs (aer mechanism).  The reference produces them in its liq_parm
+# chain (kpp.f90:516-657): henry_a 1914, v_mean_a 1472, st_coeff_a 857, fast_k_mt_a
+# 2683, equil_co_a 3162, cw_rc 2152.  That chain is "next" row N2; until
+# it lands the generator restates its tables for a mono-disperse aerosol per bin
+# (effective radius r, liquid water content cw) with activity coefficients = 1.
+# Tables below: (k_H^cp at 298 K in M/atm, -dlnk/d(1/T)), molar mass in kg/mol,
+# accommodation coefficient (temperature dependence dropped where it is weak).
+HENRY = {"NO": (1.9e-3, 1480.), "NO2": (6.4e-3, 2500.), "HNO3": (2.5e6 / 1.5e1, 8694.),
+         "HNO4": (1.2e4, 6900.), "NH3": (58., 4085.), "SO2": (1.2, 3120.), "O3": (1.2e-2, 2560.),
+         "ACO2": (3.7e3, 5700.), "ACTA": (4.1e3, 6300.), "HCHO": (7.0e3, 6425.), "ALD2": (1.3e1, 5700.),
+         "H2O2": (1.0e5, 6338.), "ROOH": (3.0e2, 5322.), "HONO": (4.9e1, 4780.), "PAN": (2.8, 6500.),
+         "HCl": (2. / 1.7, 9001.), "NO3": (2., 2000.), "DMS": (4.8e-1, 3100.), "DMSO": (5.e4, 6425.),
+         "HOCl": (6.7e2, 5862.), "Cl2": (9.1e-2, 2500.), "HBr": (1.3, 10239.), "Br2": (7.6e-1, 4094.),
+         "BrCl": (9.4e-1, 5600.), "HOBr": (9.3e1, 5862.), "I2": (3., 4431.), "HOI": (4.5e2, 5862.),
+         "ICl": (1.1e2, 5600.), "IBr": (2.4e1, 5600.), "CH3I": (1.4e-1, 4300.), "CH2I2": (2.3, 5000.),
+         "CH2ClI": (8.9e-1, 4300.), "OH": (3.0e1, 4300.), "HO2": (3.9e3, 5900.), "MO2": (6., 5600.),
+         "IO": (4.5e2, 5862.), "CO2": (3.1e-2, 2423.), "CO": (9.9e-4, 1300.), "O2": (1.3e-3, 1500.),
+         "CH3OH": (1.6e2, 5600.), "C2H5OH": (1.5e2, 6400.), "H2": (7.8e-4, 500.),
+         "XOR": (1.5e2, 6400.), "SOR": (1.5e2, 6400.)}
+HENRY_CONST = {"H2SO4": 1.e16, "CH4": 1.3e-3, "C2H6": 2.0e-3, "ETHE": 4.9e-3, "C3H7I": 1.1e-1,
+               "DMSO2": 1.e16, "CH3SO2H": 1.e16, "CH3SO3H": 1.e16, "ClONO": 4.6e-2}
+MOLMASS = {"NO": 3.e-2, "NO2": 4.6e-2, "HNO3": 6.3e-2, "NH3": 1.7e-2, "SO2": 6.4e-2, "H2SO4": 9.8e-2,
+           "O3": 4.8e-2, "ACO2": 4.6e-2, "ACTA": 6.e-2, "HCHO": 3.e-2, "H2O2": 3.4e-2, "ROOH": 4.8e-2,
+           "HONO": 4.7e-2, "HCl": 3.6e-2, "N2O5": 1.08e-1, "HNO4": 7.9e-2, "NO3": 6.2e-2, "DMS": 6.2e-2,
+           "HOCl": 5.2e-2, "ClNO3": 9.7e-2, "Cl2": 7.1e-2, "HBr": 8.1e-2, "HOBr": 9.7e-2,
+           "BrNO3": 1.42e-1, "Br2": 1.6e-1, "BrCl": 1.15e-1, "HI": 1.28e-1, "HOI": 1.44e-1,
+           "I2O2": 2.86e-1, "INO2": 1.73e-1, "INO3": 1.89e-1, "I2": 2.54e-1, "ICl": 1.62e-1,
+           "IBr": 2.07e-1, "HIO3": 1.76e-1, "DMSO": 7.8e-2, "DMSO2": 9.4e-2, "CH3SO2H": 8.0e-2,
+           "CH3SO3H": 9.6e-2, "CO2": 4.4e-2, "CH3OH": 3.2e-2, "C2H5OH": 4.6e-2, "XOR": 1.09e-1,
+           "SOR": 9.4e-2, "OH": 1.7e-2, "HO2": 3.3e-2, "MO2": 4.7e-2, "O2": 3.2e-2, "IO": 1.43e-1,
+           "OIO": 1.59e-1}
+ALPHA = {"H2SO4": 0.65, "O3": 2.0e-3, "O2": 1.0e-2, "OH": 1.0e-2, "HO2": 2.0e-1, "H2O2": 0.11,
+         "NO": 5.0e-5, "NO2": 1.5e-3, "NO3": 4.0e-2, "N2O5": 0.1, "HONO": 4.0e-2, "HNO3": 0.5,
+         "NH3": 6.0e-2, "MO2": 1.0e-2, "ROOH": 5.0e-3, "HCHO": 4.0e-2, "ACO2": 1.4e-2, "ACTA": 6.7e-2,
+         "CH3OH": 5.6e-2, "C2H5OH": 4.8e-2, "CO2": 1.0e-2, "HCl": 0.1, "Cl2": 3.8e-2, "HBr": 3.0e-2,
+         "HOBr": 0.6, "HOCl": 0.6, "BrNO3": 0.8, "ClNO3": 0.1, "Br2": 3.8e-2, "BrCl": 0.33,
+         "SO2": 0.11, "CH3SO3H": 7.6e-2, "DMS": 1.0e-2, "DMSO": 4.8e-2, "DMSO2": 3.0e-2,
+         "CH3SO2H": 2.0e-4, "INO3": 0.1, "HOI": 0.6, "HI": 3.6e-2, "I2": 1.0e-2, "IO": 0.5,
+         "I2O2": 0.1, "ICl": 1.0e-2, "IBr": 1.0e-2, "INO2": 0.1, "OIO": 1.0, "HIO3": 1.0e-2,
+         "XOR": 7.0e-2}
+# species exchanged between gas and aqueous phase (lex of fast_k_mt_a, kpp.f90:2683)
+LEX = ("NO2", "HNO3", "NH3", "SO2", "H2SO4", "O3", "ACO2", "HCHO", "H2O2", "HONO", "HCl", "N2O5",
+       "HNO4", "NO3", "OH", "HO2", "MO2", "CO2", "O2", "ROOH", "HOCl", "Cl2", "HBr", "HOBr", "Br2",
+       "BrCl", "DMSO", "ClNO3", "BrNO3", "CH3SO3H", "DMS", "CH3SO2H", "DMSO2", "HOI", "IO", "I2",
+       "ICl", "IBr", "OIO", "INO2", "INO3", "HI", "I2O2", "HIO3", "NO", "ACTA", "CH3OH", "C2H5OH",
+       "XOR", "SOR")
+# acid-base / halogen equilibria: species -> (kef0, kef T-coefficient or None, keb0, keb T-coeff or
+# None, keb multiplied by cv2?, kef multiplied by cv2?)   (equil_co_a, kpp.f90:3162-3368)
+EQUIL = {"H2O": (1.0e-5, -6716., 1.0e9, None, True, False), "HO2": (1.6e5, None, 1.e10, None, True, False),
+         "ACO2": (1.8, None, 1.0e4, None, True, False), "CO2": (4.3e-2, -913., 1.0e5, None, True, False),
+         "HONO": (5.1e3, -1260., 1.0e7, None, True, False), "HNO3": (1.54e10, 8700., 1.0e9, None, True, False),
+         "HNO4": (2.0e3, None, 2.0e8, None, True, False), "NH3": (1.7e5, -4325., 1.0e10, None, True, False),
+         "HSO3ml%d": (6.0e2, 1120., 1.0e10, None, True, False), "H2SO4": (1.0e12, None, 1.0e9, None, True, False),
+         "HSO4ml%d": (1.02e6, 2720., 1.0e8, None, True, False), "SO2": (1.7e8, 2090., 1.0e10, None, True, False),
+         "HCHO": (1.e10, None, 1.e5, None, False, True), "HCl": (1.7e10, 6896., 1.0e4, None, True, False),
+         "Cl2ml%d": (5.2e4, None, 1.e10, None, True, False), "HOCl": (3.2e2, None, 1.0e10, None, True, False),
+         "HBr": (1.0e13, None, 1.0e4, None, True, False), "Br2": (2.95e4, -4068., 1.17e10, -1812., True, False),
+         "HOBr": (2.3e1, -3091., 1.0e10, None, True, False),
+         "BrCl2ml%d": (5.e9, 1143., 1.3e9, None, False, True), "Br2Clml%d": (5.e9, None, 2.8e5, None, False, True),
+         "Br2l%d": (5.e9, None, 3.85e9, None, False, True), "ICl": (1.0e11, None, 1.3e9, None, False, True),
+         "IBr": (1.0e11, None, 3.5e8, None, False, True), "IClBrml%d": (5.e9, None, 2.8e5, None, False, True),
+         "I2": (5.e9, None, 3.85e9, None, False, True), "HIO3": (1.57e4, None, 1.0e5, None, True, False)}
+
+
+class AerEnsemble:
+    """Per-cell inputs of the aer mechanism (gas + aqueous chemistry in aerosol bins
+    1 = sulfate, 2 = sea salt) for the layers below nf of `ncol` columns: 98 cells per
+    column (k = 2..99; kpp.f90:4381-4391 - layers k >= nf are always gas-only)."""
+
+    LAYERS = NF - 2
+
+    def __init__(self, ncol, seed=SEED, halo=True, iod=True, f32_literals=1, col0=0):
+        g = GasEnsemble(ncol, seed=seed, halo=halo, iod=iod, f32_literals=f32_literals, col0=col0)
+        self.mech = 1
+        m = self.m = mechmod.load("aer")
+        self.f32 = f32_literals
+        nspec = m.nvar + m.nfix
+        idx = self.idx = {n: i for i, n in enumerate(m.spc_names)}
+        L = self.LAYERS
+        sel = (np.arange(ncol)[:, None] * CELLS_PER_COLUMN + np.arange(L)[None, :]).reshape(-1)
+        ncell = self.ncell = ncol * L
+        self.ncol = ncol
+        self.cb1 = g.cb1[sel]
+        self.ph_rat = g.ph_rat[sel]
+        tt, pk = self.cb1[:, 1], self.cb1[:, 3]
+        f32 = (lambda x: float(np.float32(x))) if f32_literals else float
+        # liquid water and effective radius per bin
+        aq = np.empty((ncol, 6))
+        for c in range(ncol):
+            aq[c] = np.random.default_rng([seed, col0 + c, 1]).uniform(0.0, 1.0, 6)
+        aq = np.repeat(aq, L, axis=0)
+        cw = np.stack([10.0 ** (-11.5 + aq[:, 0]), 10.0 ** (-10.5 + aq[:, 1])], axis=1)   # m3/m3
+        rr = np.stack([8.0e-8 * 5.0 ** aq[:, 2], 8.0e-7 * 5.0 ** aq[:, 3]], axis=1)       # m
+        cv2 = 1.0e-3 / cw                                                                # conv2
+        self.ycw = cw
+        scal = np.zeros((ncell, 13))
+        scal[:, 0] = CONV1
+        scal[:, 1] = 1.0 if halo else 0.0
+        scal[:, 2] = 1.0 if iod else 0.0
+        scal[:, 5:7] = 1.0                      # xliq1 = xliq2 = 1 -> xhet1 = xhet2 = 0
+        scal[:, 9:11] = cv2
+        self.scal = scal
+        # inverse dimensionless Henry constants (henry_a)
+        tfact = 1.0 / tt - 3.3540e-3
+        fct = 0.0820577 * tt
+        yhenry = np.zeros((ncell, nspec))
+        for s, (a0, b0) in HENRY.items():
+            if s in idx:
+                yhenry[:, idx[s]] = 1.0 / (a0 * np.exp(b0 * tfact) * fct)
+        for s, a0 in HENRY_CONST.items():
+            if s in idx:
+                yhenry[:, idx[s]] = 1.0 / (a0 * fct)
+        # mass-transfer coefficients (fast_k_mt_a for one radius per bin)
+        freep = 2.28e-5 * tt / pk
+        yxkmt = np.zeros((ncell, 2, nspec))
+        for s in LEX:
+            if s not in idx:
+                continue
+            vmean = np.sqrt(tt / MOLMASS.get(s, 5.0e-2)) * 4.60138
+            x1 = 4.0 / (3.0 * ALPHA.get(s, 0.1))
+            for kc in range(2):
+                yxkmt[:, kc, idx[s]] = vmean / (rr[:, kc] * (rr[:, kc] / freep + x1))
+        # equilibrium rate coefficients (equil_co_a, activity coefficients = 1)
+        ykef = np.zeros((ncell, 2, nspec))
+        ykeb = np.zeros((ncell, 2, nspec))
+        tf2 = 1.0 / tt - 3.354e-3
+        for s, (f0, fb, b0, bb, bcv, fcv) in EQUIL.items():
+            for kc in range(2):
+                name = s % (1,) if "%d" in s else s      # the reference indexes by the bin-1 name
+                if name not in idx:
+                    continue
+                kf = f0 * (np.exp(fb * tf2) if fb is not None else 1.0)
+                kb = b0 * (np.exp(bb * tf2) if bb is not None else 1.0)
+                ykef[:, kc, idx[name]] = kf * (cv2[:, kc] if fcv else 1.0)
+                ykeb[:, kc, idx[name]] = kb * (cv2[:, kc] if bcv else 1.0)
+        self.yhenry, self.yxkmt, self.ykef, self.ykeb = yhenry, yxkmt, ykef, ykeb
+        # dry-aerosol arrays are multiplied by xhet = 0 here; keep the gas ensemble's values
+        gi = g.idx
+        self.yxkmtd = np.zeros((ncell, 2, nspec))
+        self.yxeq = np.zeros((ncell, nspec))
+        for s in ("HNO3", "N2O5", "NH3", "H2SO4"):
+            self.yxkmtd[:, :, idx[s]] = g.yxkmtd[sel][:, :, gi[s]]
+        self.yxeq[:, idx["HNO3"]] = g.yxeq[sel][:, gi["HNO3"]]
+        self.ycwd = g.ycwd[sel]
+        # FIX = O2, H2O, N2, H2Ol1, H2Ol2 with FIX(H2Olz) = 55.55/cvvz (aer.f:197-206)
+        assert m.spc_names[m.nvar:] == ["O2", "H2O", "N2", "H2Ol1", "H2Ol2"]
+        gf = g.fix[sel]
+        self.fix = np.concatenate([gf, f32(55.55) / cv2], axis=1)
+        # VAR: gas phase from the gas ensemble (by name), ions per initc (kpp.f90:337-381)
+        var = np.zeros((ncell, m.nvar))
+        for s, i in gi.items():
+            if i < g.m.nvar and s in idx and idx[s] < m.nvar and not s.endswith(("l1", "l2")):
+                var[:, idx[s]] = g.var[sel][:, i]
+        x0 = (2.0 + 4.0 * aq[:, 4:6]) * 1.0e3 * cw          # mol/m3(air): 2..6 mol/l of salt
+        xi = 1.0 if iod else 0.0
+        for s, f in (("NH4pl1", 1.34), ("SO42ml1", 0.34), ("NO3ml1", 0.004), ("HSO4ml1", 0.656)):
+            var[:, idx[s]] = f * x0[:, 0]
+        xso4, xhco3, xno3, xbr = 0.0485, 4.2e-3, 1.0e-7, 1.45e-3
+        xim, xio3 = 7.4e-8 / 0.545 * xi, 2.64e-7 / 0.545 * xi
+        xcl = 1.0 - (xso4 + xhco3 + xno3 + xbr + xim + xio3)
+        for s, f in (("SO42ml2", xso4), ("HCO3ml2", xhco3), ("NO3ml2", xno3), ("Clml2", xcl),
+                     ("Brml2", xbr), ("Iml2", xim), ("IO3ml2", xio3), ("DOMl2", 0.27 * xbr)):
+            var[:, idx[s]] = f * x0[:, 1]
+        self.var = var
+
+    def conc(self, var=None):
+        return np.concatenate([self.var if var is None else var, self.fix], axis=1)
+
+    def rconst(self, var=None, sl=slice(None)):
+        """Update_RCONST_a for the cells in `sl` at concentrations `var`."""
+        c = self.conc(var)[sl]
+        return rc.update_rconst(1, self.cb1[sl], self.scal[sl], self.ph_rat[sl], c,
+                                yhenry=self.yhenry[sl], yxkmt=self.yxkmt[sl], ykef=self.ykef[sl],
+                                ykeb=self.ykeb[sl], yxkmtd=self.yxkmtd[sl], yxeq=self.yxeq[sl],
+                                ycw=self.ycw[sl], ycwd=self.ycwd[sl], f32_literals=self.f32)
