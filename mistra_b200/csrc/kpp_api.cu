@@ -36,9 +36,9 @@ struct DeviceState {
   // device staging for the host-buffer entry
   void *d_stage = nullptr;
   size_t d_stage_bytes = 0;
-  // pinned staging for pageable host buffers
-  void *h_stage = nullptr;
-  size_t h_stage_bytes = 0;
+  // copy streams / events of the chunk pipeline of the host-buffer entry
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h[64] = {}, ev_k[64] = {}, ev_start = nullptr;
 };
 
 constexpr int kMaxDev = 16;
@@ -332,19 +332,57 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
   int32_t *d_ie = (int32_t *)p; p += b_ie;
   int32_t *d_st = (int32_t *)p;
 
-  // Host buffers may be pageable (Fortran arrays) or pinned; cudaMemcpyAsync
-  // handles both (pinned ones overlap with the kernel of a previous call).
-  CK(cudaMemcpyAsync(d_rc, rconst, n * mi->nreact * 8, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_fx, fix, n * mi->nfix * 8, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_vr, var, n * mi->nvar * 8, cudaMemcpyHostToDevice, st));
-  rc = launch_device(*d, mech, ncell, d_rc, d_fx, d_vr, t0, t1, o, ierr ? d_ie : nullptr,
-                     stats ? d_st : nullptr, hexit ? d_hx : nullptr, texit ? d_tx : nullptr, st);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(var, d_vr, n * mi->nvar * 8, cudaMemcpyDeviceToHost, st));
-  if (ierr) CK(cudaMemcpyAsync(ierr, d_ie, n * 4, cudaMemcpyDeviceToHost, st));
-  if (stats) CK(cudaMemcpyAsync(stats, d_st, n * 32, cudaMemcpyDeviceToHost, st));
-  if (hexit) CK(cudaMemcpyAsync(hexit, d_hx, n * 8, cudaMemcpyDeviceToHost, st));
-  if (texit) CK(cudaMemcpyAsync(texit, d_tx, n * 8, cudaMemcpyDeviceToHost, st));
+  // Pipeline over chunks of cells: H2D of chunk c+1 and D2H of chunk c-1 overlap the
+  // kernel of chunk c (copy streams + events; kernels stay in order on `st`, so the
+  // lane workspace and the cell counter are never shared by two running kernels).
+  // Host buffers may be pageable (Fortran arrays) or pinned; cudaMemcpyAsync handles
+  // both, only pinned ones actually overlap.
+  if ((rc = ensure_mech(*d, mech, mi, o ? (o->f32_literals ? 1 : 0) : 1, st))) return rc;
+  const int64_t resident = (int64_t)d->mech[mech].blocks * KPP_BLOCK;
+  int64_t nchunk = ncell / (4 * resident);
+  if (nchunk < 1) nchunk = 1;
+  if (nchunk > 8) nchunk = 8;
+  if (const char *e = getenv("MISTRA_KPP_CHUNKS")) {
+    int v = atoi(e);
+    if (v >= 1 && v <= 64) nchunk = v;
+  }
+  const int64_t per = (ncell + nchunk - 1) / nchunk;
+  if (!d->s_h2d) {
+    CK(cudaStreamCreateWithFlags(&d->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&d->s_d2h, cudaStreamNonBlocking));
+    for (auto &e : d->ev_h) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : d->ev_k) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&d->ev_start, cudaEventDisableTiming));
+  }
+  // the copy streams must not run ahead of work already queued on the caller's stream
+  CK(cudaEventRecord(d->ev_start, st));
+  CK(cudaStreamWaitEvent(d->s_h2d, d->ev_start, 0));
+  CK(cudaStreamWaitEvent(d->s_d2h, d->ev_start, 0));
+  for (int64_t c = 0, off = 0; off < ncell; ++c, off += per) {
+    const size_t m = (size_t)((ncell - off) < per ? (ncell - off) : per), o0 = (size_t)off;
+    CK(cudaMemcpyAsync(d_rc + o0 * mi->nreact, rconst + o0 * mi->nreact, m * mi->nreact * 8,
+                       cudaMemcpyHostToDevice, d->s_h2d));
+    CK(cudaMemcpyAsync(d_fx + o0 * mi->nfix, fix + o0 * mi->nfix, m * mi->nfix * 8,
+                       cudaMemcpyHostToDevice, d->s_h2d));
+    CK(cudaMemcpyAsync(d_vr + o0 * mi->nvar, var + o0 * mi->nvar, m * mi->nvar * 8,
+                       cudaMemcpyHostToDevice, d->s_h2d));
+    CK(cudaEventRecord(d->ev_h[c], d->s_h2d));
+    CK(cudaStreamWaitEvent(st, d->ev_h[c], 0));
+    rc = launch_device(*d, mech, (int64_t)m, d_rc + o0 * mi->nreact, d_fx + o0 * mi->nfix,
+                       d_vr + o0 * mi->nvar, t0, t1, o, ierr ? d_ie + o0 : nullptr,
+                       stats ? d_st + o0 * 8 : nullptr, hexit ? d_hx + o0 : nullptr,
+                       texit ? d_tx + o0 : nullptr, st);
+    if (rc) return rc;
+    CK(cudaEventRecord(d->ev_k[c], st));
+    CK(cudaStreamWaitEvent(d->s_d2h, d->ev_k[c], 0));
+    CK(cudaMemcpyAsync(var + o0 * mi->nvar, d_vr + o0 * mi->nvar, m * mi->nvar * 8,
+                       cudaMemcpyDeviceToHost, d->s_d2h));
+    if (ierr) CK(cudaMemcpyAsync(ierr + o0, d_ie + o0, m * 4, cudaMemcpyDeviceToHost, d->s_d2h));
+    if (stats) CK(cudaMemcpyAsync(stats + o0 * 8, d_st + o0 * 8, m * 32, cudaMemcpyDeviceToHost, d->s_d2h));
+    if (hexit) CK(cudaMemcpyAsync(hexit + o0, d_hx + o0, m * 8, cudaMemcpyDeviceToHost, d->s_d2h));
+    if (texit) CK(cudaMemcpyAsync(texit + o0, d_tx + o0, m * 8, cudaMemcpyDeviceToHost, d->s_d2h));
+  }
+  CK(cudaStreamSynchronize(d->s_d2h));
   CK(cudaStreamSynchronize(st));
   return 0;
 }
@@ -367,7 +405,13 @@ int mistra_kpp_finalize(void)
     }
     if (d.counter) cudaFree(d.counter);
     if (d.d_stage) cudaFree(d.d_stage);
-    if (d.h_stage) cudaFreeHost(d.h_stage);
+    if (d.s_h2d) {
+      cudaStreamDestroy(d.s_h2d);
+      cudaStreamDestroy(d.s_d2h);
+      for (auto &e : d.ev_h) cudaEventDestroy(e);
+      for (auto &e : d.ev_k) cudaEventDestroy(e);
+      cudaEventDestroy(d.ev_start);
+    }
     if (d.stream) cudaStreamDestroy(d.stream);
     d = DeviceState();
   }
