@@ -51,6 +51,9 @@ def parse_args():
                     help="columns per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bins", action="store_true")
+    ap.add_argument("--bins-layers", type=int, default=int(os.environ.get("MISTRA_BENCH_BINS_LAYERS", "29600")),
+                    help="layers per GPU for the 2-D bin redistribution leg (200 columns x 148)")
     return ap.parse_args()
 
 
@@ -383,6 +386,10 @@ def run_b200(args):
                "value_1thread": c_1 / t_1, "sample_1thread": "%d cells, %.1f s" % (c_1, t_1),
                "note": "C restatement of the reference Fortran (no Fortran compiler in the image)"}
 
+    bins_res = None
+    if not args.no_bins:
+        bins_res = run_bins_leg(args, dev, world, rank, barrier)
+
     if rank == 0:
         clocks = clk.summary()
         line = {
@@ -401,6 +408,7 @@ def run_b200(args):
             "diagnostics": {"sum_nstp": float(diag[0]), "sum_nrej": float(diag[1]),
                             "failed_cells": float(diag[2]), "cells": float(diag[3]),
                             "mean_steps_per_cell": float(diag[0] / max(1.0, float(diag[3])))},
+            "bins": bins_res,
             "per_mechanism": {k: {"kernel_ms": float(np.mean(v)),
                                   "cells_per_s": [d["n"] for d in dbatches if d["name"] == k][0] / (np.mean(v) * 1e-3)}
                               for k, v in kernel_ms.items()},
@@ -408,6 +416,88 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_bins_leg(args, dev, world, rank, barrier):
+    """Second hot-path row: the 2-D bin redistribution around the chemistry call
+    (stem_kpp, str.f90:5916-6134).  One step = snapshot + redistribute over every layer.
+    Reported beside the headline, not part of `value`."""
+    import torch
+    import torch.distributed as dist
+    from mistra_b200 import bins
+    grid = bins.particle_grid()
+    n = args.bins_layers
+    d = bins.synthetic_layers(grid, n, seed=20261018 + rank)
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in d.items()}
+    ff0, si0, sl0 = t["ff"].clone(), t["sion1_new"].clone(), t["sl1"].clone()
+    sap = torch.zeros((n, 4), dtype=torch.float64, device=dev)
+    smp = torch.zeros_like(sap)
+    so = torch.zeros((n, 4, 9), dtype=torch.float64, device=dev)
+    nw = torch.zeros(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    ev = []
+
+    def step(timed):
+        t["ff"].copy_(ff0); t["sion1_new"].copy_(si0); t["sl1"].copy_(sl0)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        bins.snapshot_device(grid, t["ff"], t["cm"], t["sion1"], sap, smp, so)
+        e1.record(stream)
+        bins.redistribute_device(grid, t["ff"], t["cm"], t["cw"], sap, smp, so, t["sion1_new"], t["sl1"], nw)
+        e2.record(stream)
+        if timed:
+            ev.append((e0, e1, e2))
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    l0 = bins.launch_count()
+    for _ in range(args.steps):
+        step(True)
+    barrier()
+    launches = bins.launch_count() - l0
+    ms_snap = float(np.mean([a.elapsed_time(b) for a, b, _ in ev]))
+    ms_red = float(np.mean([b.elapsed_time(c) for _, b, c in ev]))
+    tt = torch.tensor([ms_snap + ms_red], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    peaks, peak_src = measured_peaks()
+    tile = grid["nka"] * grid["nkt"] * 8
+    bytes_red = n * (2 * tile + 2 * 4 * (121 + 55) * 8)       # ff + sl1 + sion1, read and written once
+    bytes_snap = n * tile
+    res = {"metric": "bin_redistribution_layers_per_s", "value": n * world / (ms * 1e-3), "unit": "layers/s",
+           "layers_per_gpu": n, "ms_per_step": ms, "gpu_launches": int(launches),
+           "workload": "synthetic 70x70 particle spectra, 4 chem bins, +-5 % ion mass change per bin "
+                       "(%.1f GB of ff per GPU: larger than L2)" % (n * tile * 1e-9),
+           "roofline": {"bound": "hbm", "kernel": "bins_redistribute_kernel",
+                        "achieved": bytes_red / (ms_red * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": bytes_red / (ms_red * 1e-3) * 1e-9 / peaks["hbm_gbs"], "peak_source": peak_src,
+                        "kernel_ms": ms_red, "traffic": None,
+                        "note": "algorithmic bytes per layer = 2*(nka*nkt + 4*(j2+j6))*8 = %d B" % (bytes_red // n),
+                        "snapshot": {"kernel": "bins_snapshot_kernel", "kernel_ms": ms_snap,
+                                     "achieved": bytes_snap / (ms_snap * 1e-3) * 1e-9,
+                                     "frac": bytes_snap / (ms_snap * 1e-3) * 1e-9 / peaks["hbm_gbs"]}}}
+    if not args.no_e2e:
+        h = {k: np.ascontiguousarray(v) for k, v in d.items()}
+        t0 = time.perf_counter()
+        reps = max(1, min(args.steps, 3))
+        for _ in range(reps):
+            s_, m_, o_ = bins.snapshot(grid, h["ff"], h["cm"], h["sion1"])
+            bins.redistribute(grid, h["ff"], h["cm"], h["cw"], s_, m_, o_, h["sion1_new"], h["sl1"])
+        dt = (time.perf_counter() - t0) / reps
+        res["e2e"] = {"value": n * world / dt, "unit": "layers/s", "ms_per_step": dt * 1e3,
+                      "h2d_bytes_per_step": int(2 * n * tile + n * 8 * (4 * 4 + 2 * 4 * 55 + 2 * 4 * 9 + 4 * 121)),
+                      "d2h_bytes_per_step": int(n * tile + n * 8 * (2 * 4 + 4 * 9 + 4 * 55 + 4 * 121) + 4 * n)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import bins_oracle as bo
+        m = min(n, 4000)
+        t0 = time.perf_counter()
+        s_, m_, o_ = bo.snapshot(grid, d["ff"][:m], d["cm"][:m], d["sion1"][:m])
+        bo.redistribute(grid, d["ff"][:m], d["cm"][:m], d["cw"][:m], s_, m_, o_, d["sion1_new"][:m], d["sl1"][:m])
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": m / dt, "unit": "layers/s", "cores": 1, "kind": "port",
+                               "sample": "%d layers, single thread (as the reference runs), %.2f s" % (m, dt)}
+    return res
 
 
 def main():

@@ -28,7 +28,8 @@ HOSTCXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", HOSTCXX]
 
-UNITS = ["kpp_mech_g.cu", "kpp_mech_a.cu", "kpp_mech_t.cu", "kpp_api.cu", "_gen/kpp_names.cpp"]
+UNITS = ["kpp_mech_g.cu", "kpp_mech_a.cu", "kpp_mech_t.cu", "kpp_api.cu", "bins_kernels.cu",
+         "_gen/kpp_names.cpp"]
 
 
 def _hash(paths, extra):
@@ -43,6 +44,8 @@ def _hash(paths, extra):
 def _deps(unit):
     deps = [os.path.join(CSRC, unit), os.path.join(CSRC, "kpp_batch.h"),
             os.path.join(ROOT, "include", "mistra_kpp.h")]
+    if unit.startswith("bins_"):
+        deps.append(os.path.join(ROOT, "include", "mistra_bins.h"))
     if unit.startswith("kpp_mech_"):
         x = unit[len("kpp_mech_")]
         deps += [os.path.join(CSRC, "_gen", "mech_%s.cuh" % x), os.path.join(CSRC, "ros3_kernel.inc")]

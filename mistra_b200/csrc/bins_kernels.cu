@@ -1,0 +1,496 @@
+// 2-D aerosol/droplet bin redistribution around the chemistry step (include/mistra_bins.h):
+// CUDA kernels + C-ABI entries.  Role in the reference: the loop nests of SUBROUTINE
+// stem_kpp, /root/reference/src/str.f90:5916-5966 (snapshot) and 5976-6134
+// (redistribution + exchange of dissolved species).
+//
+// Mapping: one CTA per model layer ("cell"), the layer's ff(jt,ia) tile (nka x nkt
+// doubles, 39.2 kB for 70 x 70) staged in shared memory by coalesced loads, written back
+// once.  The kernels are HBM-bound: 2 x 39.2 kB (+ 11 kB of sl1/sion1) per layer-call.
+//   * Sums whose rounding feeds the result (sap, smp -> x0 -> ix/c0 -> ff) are taken in the
+//     reference's loop order by one thread per chem bin, with explicit __dadd_rn/__dmul_rn
+//     (no FMA contraction), so ff is reproduced to the last bit.
+//   * The shift along the dry-mass axis is sequential in ia (in-place, direction depends
+//     on the sign of the mass change, str.f90:6012-6021) but independent between water
+//     bins jt: one thread per jt walks ia in the reference's order.
+//   * Transferred volumes vc(tix,kc) are accumulated per jt and reduced in jt order.
+#include "../../include/mistra_bins.h"
+#include "../../include/mistra_kpp.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+int mistra_internal_fail(int code, const std::string &msg);  // kpp_api.cu
+
+namespace {
+
+constexpr int NKC = MISTRA_NKC, LSP = MISTRA_LSP, J2 = MISTRA_J2, J6 = MISTRA_J6;
+constexpr int BINS_THREADS = 128;
+constexpr int MAXK = 128;  // max nka / nkt
+
+__constant__ int c_lj2[LSP] = {1, 2, 8, 9, 13, 14, 19, 20, 30};  // str.f90:5876
+
+struct GridDev {
+  int nka, nkt, ka, nkc_l, ial_first;
+  const int *kw;
+  const double *en;
+  const double *rq;
+};
+
+__device__ __forceinline__ void ia_range(const GridDev &g, int kc, int &ial, int &iau)
+{
+  if (kc == 1 || kc == 3) { ial = g.ial_first; iau = g.ka; }  // str.f90:5924-5931
+  else { ial = g.ka + 1; iau = g.nka - 1; }                   // str.f90:5932-5935
+}
+
+// ---- str.f90:5916-5966 ---------------------------------------------------------------
+__global__ void __launch_bounds__(BINS_THREADS)
+bins_snapshot_kernel(GridDev g, long long ncell, const double *__restrict__ ff,
+                     const double *__restrict__ cm, const double *__restrict__ sion1,
+                     double *__restrict__ sap, double *__restrict__ smp,
+                     double *__restrict__ sion1o)
+{
+  extern __shared__ double sm[];
+  const int nka = g.nka, nkt = g.nkt, ntile = nka * nkt;
+  double *t_ff = sm;
+  double *s_en = sm + ntile;
+  int *s_kw = (int *)(s_en + nka);
+  for (int i = threadIdx.x; i < nka; i += blockDim.x) { s_en[i] = g.en[i]; s_kw[i] = g.kw[i]; }
+  for (long long c = blockIdx.x; c < ncell; c += gridDim.x) {
+    bool any = false;
+    for (int kc = 0; kc < g.nkc_l; ++kc) any |= (cm[c * NKC + kc] != 0.0);
+    __syncthreads();  // previous tile fully consumed
+    if (any) {
+      const double *f = ff + (size_t)c * ntile;
+      for (int i = threadIdx.x; i < ntile; i += blockDim.x) t_ff[i] = f[i];
+    }
+    __syncthreads();
+    const int kc = threadIdx.x + 1;
+    if (kc <= NKC) {
+      double sapk = 0.0, smpk = 0.0;
+      if (kc <= g.nkc_l && cm[c * NKC + kc - 1] != 0.0) {
+        int ial, iau;
+        ia_range(g, kc, ial, iau);
+        for (int ia = ial; ia <= iau; ++ia) {
+          int jtl, jtu;
+          if (kc <= 2) { jtl = 1; jtu = s_kw[ia - 1]; }
+          else { jtl = s_kw[ia - 1] + 1; jtu = nkt; }
+          const double en = s_en[ia - 1];
+          double fs = 0.0;
+          const double *row = t_ff + (ia - 1) * nkt;
+          for (int jt = jtl; jt <= jtu; ++jt) {
+            const double v = row[jt - 1];
+            fs = __dadd_rn(fs, __dmul_rn(v, en));  // str.f90:5948
+            sapk = __dadd_rn(sapk, v);             // str.f90:5949
+          }
+          smpk = __dadd_rn(smpk, fs);              // str.f90:5951
+        }
+        for (int l = 0; l < LSP; ++l)              // str.f90:5959-5962
+          sion1o[(c * NKC + kc - 1) * LSP + l] = sion1[(c * NKC + kc - 1) * J6 + c_lj2[l] - 1];
+      }
+      sap[c * NKC + kc - 1] = sapk;
+      smp[c * NKC + kc - 1] = smpk;
+    }
+  }
+}
+
+// ---- str.f90:5976-6134 ---------------------------------------------------------------
+__global__ void __launch_bounds__(BINS_THREADS)
+bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
+                         const double *__restrict__ cm, const double *__restrict__ cw,
+                         const double *__restrict__ sap, const double *__restrict__ smp,
+                         const double *__restrict__ sion1o, double *__restrict__ sion1,
+                         double *__restrict__ sl1, int *__restrict__ nwarn)
+{
+  extern __shared__ double sm[];
+  const int nka = g.nka, nkt = g.nkt, ntile = nka * nkt;
+  double *t_ff = sm;                         // [nka][nkt]
+  double *s_en = t_ff + ntile;               // [nka]
+  double *s_c0 = s_en + nka;                 // [NKC][nka]
+  double *s_vcp = s_c0 + NKC * nka;          // [NKC*NKC][nkt] per-jt partial volumes
+  double *s_vc = s_vcp + NKC * NKC * nkt;    // [NKC*NKC]
+  double *s_den = s_vc + NKC * NKC;          // [NKC]
+  int *s_kw = (int *)(s_den + NKC);          // [nka]
+  int *s_ix = s_kw + nka;                    // [NKC][nka]
+  int *s_act = s_ix + NKC * nka;             // [NKC] + warn counter
+  const double fpi = 4.0 / 3.0 * 3.1415926535897932;  // str.f90:5838
+  const double em6 = (double)1.e-06f;                  // default-REAL literal of str.f90:5983
+  for (int i = threadIdx.x; i < nka; i += blockDim.x) { s_en[i] = g.en[i]; s_kw[i] = g.kw[i]; }
+
+  for (long long c = blockIdx.x; c < ncell; c += gridDim.x) {
+    __syncthreads();
+    // ---- phase 0: mass change per particle of every bin (str.f90:5979-5993) ----
+    if (threadIdx.x < NKC) {
+      const int kc = threadIdx.x + 1;
+      int act = 0;
+      double den = 0.0;
+      if (kc <= g.nkc_l && cm[c * NKC + kc - 1] != 0.0 && sap[c * NKC + kc - 1] > 1.e-6) {
+        act = 1;
+        const double sapk = sap[c * NKC + kc - 1];
+        double ds[LSP];
+        for (int l = 0; l < LSP; ++l) {
+          const double d = __dadd_rn(sion1[(c * NKC + kc - 1) * J6 + c_lj2[l] - 1],
+                                     -sion1o[(c * NKC + kc - 1) * LSP + l]);
+          ds[l] = __ddiv_rn(__dmul_rn(d, em6), sapk);
+        }
+        const double mw[LSP] = {1., 18., 96., 44., 62., 35.5, 97., 23., 95.};
+        double s = __dmul_rn(ds[0], mw[0]);
+        for (int l = 1; l < LSP; ++l) s = __dadd_rn(s, __dmul_rn(ds[l], mw[l]));
+        den = __dmul_rn(s, 1000.);
+      }
+      s_act[threadIdx.x] = act;
+      s_den[threadIdx.x] = den;
+    }
+    if (threadIdx.x == NKC) s_act[NKC] = 0;  // warn counter
+    for (int i = threadIdx.x; i < NKC * NKC * nkt; i += blockDim.x) s_vcp[i] = 0.0;
+    __syncthreads();
+    const bool any = s_act[0] | s_act[1] | s_act[2] | s_act[3];
+    if (any) {
+      double *f = ff + (size_t)c * ntile;
+      for (int i = threadIdx.x; i < ntile; i += blockDim.x) t_ff[i] = f[i];
+      // ---- phase 1: target class ix and split c0 of every (kc, ia) (str.f90:6023-6044) ----
+      for (int p = threadIdx.x; p < NKC * nka; p += blockDim.x) {
+        const int kc = p / nka + 1, ia = p % nka + 1;
+        int ix = 0;
+        double c0 = 0.0;
+        if (s_act[kc - 1]) {
+          int ial, iau;
+          ia_range(g, kc, ial, iau);
+          if (ia >= ial && ia <= iau) {
+            const double den = s_den[kc - 1], en = s_en[ia - 1];
+            const double x0 = __dadd_rn(en, __dmul_rn(__ddiv_rn(__dmul_rn(den, en), smp[c * NKC + kc - 1]),
+                                                      sap[c * NKC + kc - 1]));
+            if (!(den > 0.0) && x0 <= 0.0) atomicAdd(&s_act[NKC], 1);
+            for (int iia = 1; iia <= nka - 1; ++iia) {
+              if (s_en[iia - 1] <= x0 && s_en[iia] > x0) {
+                ix = iia;
+                c0 = __ddiv_rn(__dadd_rn(s_en[iia], -x0), __dadd_rn(s_en[iia], -s_en[iia - 1]));
+                break;
+              }
+            }
+            if (ix == 0) {
+              if (s_en[0] > x0) { ix = 1; c0 = 1.0; }
+              else { ix = nka - 1; c0 = 0.0; }
+            }
+          }
+        }
+        s_ix[p] = ix;
+        s_c0[p] = c0;
+      }
+      __syncthreads();
+      // ---- phase 2: one thread per water bin jt walks the dry classes (str.f90:6012-6096) ----
+      const int jt = threadIdx.x + 1;
+      if (jt <= nkt) {
+        for (int kc = 1; kc <= g.nkc_l; ++kc) {
+          if (!s_act[kc - 1]) continue;
+          int ial, iau;
+          ia_range(g, kc, ial, iau);
+          int istart = ial, iend = iau, iinkr = 1;
+          if (s_den[kc - 1] >= 0.0) { istart = iau; iend = ial; iinkr = -1; }
+          for (int ia = istart; iinkr > 0 ? ia <= iend : ia >= iend; ia += iinkr) {
+            const int kwa = s_kw[ia - 1];
+            const bool mine = (kc <= 2) ? (jt <= kwa) : (jt > kwa);
+            if (!mine) continue;
+            const double x1 = t_ff[(ia - 1) * nkt + jt - 1];
+            if (x1 > 0.0) {
+              const int ix = s_ix[(kc - 1) * nka + ia - 1];
+              const double c0 = s_c0[(kc - 1) * nka + ia - 1];
+              const double a = __dmul_rn(x1, c0), b = __dmul_rn(x1, __dadd_rn(1.0, -c0));
+              t_ff[(ia - 1) * nkt + jt - 1] = 0.0;
+              t_ff[(ix - 1) * nkt + jt - 1] = __dadd_rn(t_ff[(ix - 1) * nkt + jt - 1], a);
+              t_ff[ix * nkt + jt - 1] = __dadd_rn(t_ff[ix * nkt + jt - 1], b);
+              int tix, tixp;
+              if (ix > g.ka) tix = (jt > s_kw[ix - 1]) ? 4 : 2;
+              else tix = (jt > s_kw[ix - 1]) ? 3 : 1;
+              if (ix + 1 > g.ka) tixp = (jt > s_kw[ix]) ? 4 : 2;
+              else tixp = (jt > s_kw[ix]) ? 3 : 1;
+              const double r = g.rq[(ia - 1) * nkt + jt - 1];
+              const double r3 = __dmul_rn(__dmul_rn(r, r), r);
+              if (tix != kc) {
+                double *v = &s_vcp[((kc - 1) * NKC + tix - 1) * nkt + jt - 1];
+                *v = __dadd_rn(*v, __dmul_rn(__dmul_rn(a, fpi), r3));
+              }
+              if (tixp != kc) {
+                double *v = &s_vcp[((kc - 1) * NKC + tixp - 1) * nkt + jt - 1];
+                *v = __dadd_rn(*v, __dmul_rn(__dmul_rn(b, fpi), r3));
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      // ---- phase 3: transferred volume per (from, to) pair, summed in jt order ----
+      if (threadIdx.x < NKC * NKC) {
+        double s = 0.0;
+        for (int j = 0; j < nkt; ++j) s = __dadd_rn(s, s_vcp[threadIdx.x * nkt + j]);
+        s_vc[threadIdx.x] = s;
+      }
+      for (int i = threadIdx.x; i < ntile; i += blockDim.x) f[i] = t_ff[i];
+      __syncthreads();
+      // ---- phase 4: exchange of dissolved species between bins (str.f90:6102-6134) ----
+      for (int pass = 0; pass < 2; ++pass) {
+        const int nl = pass == 0 ? J2 : J6;
+        double *base = (pass == 0 ? sl1 : sion1) + (size_t)c * NKC * nl;
+        for (int l = threadIdx.x; l < nl; l += blockDim.x) {
+          double v[NKC];
+          for (int k = 0; k < NKC; ++k) v[k] = base[k * nl + l];
+          bool touched = false;
+          for (int kc = 0; kc < g.nkc_l; ++kc)
+            for (int kkc = 0; kkc < g.nkc_l; ++kkc) {
+              if (kkc == kc) continue;
+              const double vcv = s_vc[kc * NKC + kkc];
+              if (vcv == 0.0) continue;
+              const double cwf = cw[c * NKC + kc];
+              if (cwf > 0.0) {
+                const double vol_ch = __dmul_rn(vcv, 1.e-12);
+                const double xfact = __dadd_rn(1.0, -__ddiv_rn(__dadd_rn(cwf, -vol_ch), cwf));
+                const double xch = __dmul_rn(v[kc], xfact);
+                v[kc] = __dadd_rn(v[kc], -xch);
+                v[kkc] = __dadd_rn(v[kkc], xch);
+                touched = true;
+              }
+            }
+          if (touched)
+            for (int k = 0; k < NKC; ++k) base[k * nl + l] = v[k];
+        }
+      }
+    }
+    if (nwarn && threadIdx.x == 0) nwarn[c] = any ? s_act[NKC] : 0;
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------
+std::mutex g_mu;
+std::atomic<long long> g_launches{0};
+
+struct GridCache {
+  bool valid = false;
+  int nka = 0, nkt = 0;
+  std::vector<int> kw;
+  std::vector<double> en, rq;
+  int *d_kw = nullptr;
+  double *d_en = nullptr, *d_rq = nullptr;
+  int num_sm = 0;
+  bool attr_set = false;
+};
+GridCache g_cache[16];
+
+#define CKB(call)                                                                      \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return mistra_internal_fail(e_ == cudaErrorMemoryAllocation ? MISTRA_KPP_ENOMEM  \
+                                  : (e_ == cudaErrorNoDevice ? MISTRA_KPP_ENODEVICE    \
+                                                             : MISTRA_KPP_ECUDA),      \
+                                  std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+int check_grid(const mistra_bins_grid *g)
+{
+  if (!g || !g->kw || !g->en || !g->rq) return mistra_internal_fail(MISTRA_KPP_EINVAL, "null grid");
+  if (g->nka < 2 || g->nka > MAXK || g->nkt < 1 || g->nkt > BINS_THREADS)
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "grid size out of range (nka <= 128, nkt <= 128)");
+  if (g->nkc_l < 1 || g->nkc_l > NKC || g->ka < 0 || g->ka > g->nka || g->ial_first < 1 || g->ial_first > 2)
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad ka / nkc_l / ial_first");
+  for (int i = 0; i < g->nka; ++i)
+    if (g->kw[i] < 0 || g->kw[i] > g->nkt) return mistra_internal_fail(MISTRA_KPP_EINVAL, "kw out of range");
+  return 0;
+}
+
+// upload the grid arrays once per distinct grid (stream-ordered; a changed grid waits for
+// the kernels that still read the old one)
+int grid_to_device(const mistra_bins_grid *g, cudaStream_t st, GridDev *out, GridCache **cache)
+{
+  int dev = -1;
+  CKB(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return mistra_internal_fail(MISTRA_KPP_ENODEVICE, "device index out of range");
+  GridCache &gc = g_cache[dev];
+  const size_t nrq = (size_t)g->nka * g->nkt;
+  const bool same = gc.valid && gc.nka == g->nka && gc.nkt == g->nkt &&
+                    !memcmp(gc.kw.data(), g->kw, sizeof(int) * g->nka) &&
+                    !memcmp(gc.en.data(), g->en, sizeof(double) * g->nka) &&
+                    !memcmp(gc.rq.data(), g->rq, sizeof(double) * nrq);
+  if (!same) {
+    if (!gc.d_kw) {
+      cudaDeviceProp p;
+      CKB(cudaGetDeviceProperties(&p, dev));
+      gc.num_sm = p.multiProcessorCount;
+      CKB(cudaMalloc(&gc.d_kw, sizeof(int) * MAXK));
+      CKB(cudaMalloc(&gc.d_en, sizeof(double) * MAXK));
+      CKB(cudaMalloc(&gc.d_rq, sizeof(double) * MAXK * MAXK));
+    }
+    if (gc.valid) CKB(cudaDeviceSynchronize());
+    gc.kw.assign(g->kw, g->kw + g->nka);
+    gc.en.assign(g->en, g->en + g->nka);
+    gc.rq.assign(g->rq, g->rq + nrq);
+    gc.nka = g->nka;
+    gc.nkt = g->nkt;
+    CKB(cudaMemcpyAsync(gc.d_kw, gc.kw.data(), sizeof(int) * g->nka, cudaMemcpyHostToDevice, st));
+    CKB(cudaMemcpyAsync(gc.d_en, gc.en.data(), sizeof(double) * g->nka, cudaMemcpyHostToDevice, st));
+    CKB(cudaMemcpyAsync(gc.d_rq, gc.rq.data(), sizeof(double) * nrq, cudaMemcpyHostToDevice, st));
+    CKB(cudaStreamSynchronize(st));
+    gc.valid = true;
+  }
+  if (!gc.attr_set) {
+    CKB(cudaFuncSetAttribute(bins_snapshot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKB(cudaFuncSetAttribute(bins_redistribute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    gc.attr_set = true;
+  }
+  out->nka = g->nka; out->nkt = g->nkt; out->ka = g->ka; out->nkc_l = g->nkc_l;
+  out->ial_first = g->ial_first;
+  out->kw = gc.d_kw; out->en = gc.d_en; out->rq = gc.d_rq;
+  *cache = &gc;
+  return 0;
+}
+
+size_t smem_snapshot(const mistra_bins_grid *g)
+{
+  return sizeof(double) * ((size_t)g->nka * g->nkt + g->nka) + sizeof(int) * g->nka;
+}
+size_t smem_redistribute(const mistra_bins_grid *g)
+{
+  const size_t nka = g->nka, nkt = g->nkt;
+  return sizeof(double) * (nka * nkt + nka + NKC * nka + NKC * NKC * nkt + NKC * NKC + NKC) +
+         sizeof(int) * (nka + NKC * nka + NKC + 4);
+}
+
+int grid_blocks(const GridCache &gc, int64_t ncell, size_t smem)
+{
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  long long b = (long long)gc.num_sm * per_sm;
+  return (int)(ncell < b ? ncell : b);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mistra_bins_snapshot_device(const mistra_bins_grid *g, int64_t ncell, const double *d_ff,
+                                const double *d_cm, const double *d_sion1, double *d_sap,
+                                double *d_smp, double *d_sion1o, void *stream)
+{
+  int rc = check_grid(g);
+  if (rc) return rc;
+  if (ncell < 0) return mistra_internal_fail(MISTRA_KPP_EINVAL, "ncell < 0");
+  if (ncell == 0) return 0;
+  if (!d_ff || !d_cm || !d_sion1 || !d_sap || !d_smp || !d_sion1o)
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "null array");
+  std::lock_guard<std::mutex> lk(g_mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  GridDev gd;
+  GridCache *gc;
+  if ((rc = grid_to_device(g, st, &gd, &gc))) return rc;
+  const size_t smem = smem_snapshot(g);
+  bins_snapshot_kernel<<<grid_blocks(*gc, ncell, smem), BINS_THREADS, smem, st>>>(
+      gd, ncell, d_ff, d_cm, d_sion1, d_sap, d_smp, d_sion1o);
+  CKB(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mistra_bins_redistribute_device(const mistra_bins_grid *g, int64_t ncell, double *d_ff,
+                                    const double *d_cm, const double *d_cw, const double *d_sap,
+                                    const double *d_smp, const double *d_sion1o, double *d_sion1,
+                                    double *d_sl1, int32_t *d_nwarn, void *stream)
+{
+  int rc = check_grid(g);
+  if (rc) return rc;
+  if (ncell < 0) return mistra_internal_fail(MISTRA_KPP_EINVAL, "ncell < 0");
+  if (ncell == 0) return 0;
+  if (!d_ff || !d_cm || !d_cw || !d_sap || !d_smp || !d_sion1o || !d_sion1 || !d_sl1)
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "null array");
+  std::lock_guard<std::mutex> lk(g_mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  GridDev gd;
+  GridCache *gc;
+  if ((rc = grid_to_device(g, st, &gd, &gc))) return rc;
+  const size_t smem = smem_redistribute(g);
+  bins_redistribute_kernel<<<grid_blocks(*gc, ncell, smem), BINS_THREADS, smem, st>>>(
+      gd, ncell, d_ff, d_cm, d_cw, d_sap, d_smp, d_sion1o, d_sion1, d_sl1, d_nwarn);
+  CKB(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+// Host-buffer entries: stage, run, copy back (synchronous).
+int mistra_bins_snapshot(const mistra_bins_grid *g, int64_t ncell, const double *ff,
+                         const double *cm, const double *sion1, double *sap, double *smp,
+                         double *sion1o, void *stream)
+{
+  int rc = check_grid(g);
+  if (rc) return rc;
+  if (ncell < 0) return mistra_internal_fail(MISTRA_KPP_EINVAL, "ncell < 0");
+  if (ncell == 0) return 0;
+  if (!ff || !cm || !sion1 || !sap || !smp || !sion1o) return mistra_internal_fail(MISTRA_KPP_EINVAL, "null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)ncell, tile = (size_t)g->nka * g->nkt;
+  const size_t b_ff = n * tile * 8, b_c = n * NKC * 8, b_si = n * NKC * J6 * 8, b_so = n * NKC * LSP * 8;
+  char *d = nullptr;
+  CKB(cudaMalloc(&d, b_ff + 3 * b_c + b_si + b_so));
+  double *d_ff = (double *)d, *d_cm = (double *)(d + b_ff), *d_sap = d_cm + n * NKC, *d_smp = d_sap + n * NKC;
+  double *d_si = d_smp + n * NKC, *d_so = (double *)((char *)d_si + b_si);
+  auto done = [&](int r) { cudaFree(d); return r; };
+#define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(mistra_internal_fail(MISTRA_KPP_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
+  CKF(cudaMemcpyAsync(d_ff, ff, b_ff, cudaMemcpyHostToDevice, st));
+  CKF(cudaMemcpyAsync(d_cm, cm, b_c, cudaMemcpyHostToDevice, st));
+  CKF(cudaMemcpyAsync(d_si, sion1, b_si, cudaMemcpyHostToDevice, st));
+  CKF(cudaMemcpyAsync(d_so, sion1o, b_so, cudaMemcpyHostToDevice, st));  // entries of inactive bins stay as given
+  if ((rc = mistra_bins_snapshot_device(g, ncell, d_ff, d_cm, d_si, d_sap, d_smp, d_so, stream))) return done(rc);
+  CKF(cudaMemcpyAsync(sap, d_sap, b_c, cudaMemcpyDeviceToHost, st));
+  CKF(cudaMemcpyAsync(smp, d_smp, b_c, cudaMemcpyDeviceToHost, st));
+  CKF(cudaMemcpyAsync(sion1o, d_so, b_so, cudaMemcpyDeviceToHost, st));
+  CKF(cudaStreamSynchronize(st));
+  return done(0);
+}
+
+int mistra_bins_redistribute(const mistra_bins_grid *g, int64_t ncell, double *ff,
+                             const double *cm, const double *cw, const double *sap,
+                             const double *smp, const double *sion1o, double *sion1,
+                             double *sl1, int32_t *nwarn, void *stream)
+{
+  int rc = check_grid(g);
+  if (rc) return rc;
+  if (ncell < 0) return mistra_internal_fail(MISTRA_KPP_EINVAL, "ncell < 0");
+  if (ncell == 0) return 0;
+  if (!ff || !cm || !cw || !sap || !smp || !sion1o || !sion1 || !sl1)
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)ncell, tile = (size_t)g->nka * g->nkt;
+  const size_t b_ff = n * tile * 8, b_c = n * NKC * 8, b_si = n * NKC * J6 * 8, b_so = n * NKC * LSP * 8,
+               b_sl = n * NKC * J2 * 8, b_w = n * 4;
+  char *d = nullptr;
+  CKB(cudaMalloc(&d, b_ff + 4 * b_c + b_si + b_so + b_sl + b_w));
+  double *d_ff = (double *)d, *d_cm = (double *)(d + b_ff), *d_cw = d_cm + n * NKC, *d_sap = d_cw + n * NKC,
+         *d_smp = d_sap + n * NKC;
+  double *d_si = d_smp + n * NKC, *d_so = (double *)((char *)d_si + b_si), *d_sl = (double *)((char *)d_so + b_so);
+  int32_t *d_w = (int32_t *)((char *)d_sl + b_sl);
+  auto done = [&](int r) { cudaFree(d); return r; };
+  CKF(cudaMemcpyAsync(d_ff, ff, b_ff, cudaMemcpyHostToDevice, st));
+  CKF(cudaMemcpyAsync(d_cm, cm, b_c, cudaMemcpyHostToDevice, st));
+  CKF(cudaMemcpyAsync(d_cw, cw, b_c, cudaMemcpyHostToDevice, st));
+  CKF(cudaMemcpyAsync(d_sap, sap, b_c, cudaMemcpyHostToDevice, st));
+  CKF(cudaMemcpyAsync(d_smp, smp, b_c, cudaMemcpyHostToDevice, st));
+  CKF(cudaMemcpyAsync(d_si, sion1, b_si, cudaMemcpyHostToDevice, st));
+  CKF(cudaMemcpyAsync(d_so, sion1o, b_so, cudaMemcpyHostToDevice, st));
+  CKF(cudaMemcpyAsync(d_sl, sl1, b_sl, cudaMemcpyHostToDevice, st));
+  if ((rc = mistra_bins_redistribute_device(g, ncell, d_ff, d_cm, d_cw, d_sap, d_smp, d_so, d_si, d_sl,
+                                            nwarn ? d_w : nullptr, stream)))
+    return done(rc);
+  CKF(cudaMemcpyAsync(ff, d_ff, b_ff, cudaMemcpyDeviceToHost, st));
+  CKF(cudaMemcpyAsync(sion1, d_si, b_si, cudaMemcpyDeviceToHost, st));
+  CKF(cudaMemcpyAsync(sl1, d_sl, b_sl, cudaMemcpyDeviceToHost, st));
+  if (nwarn) CKF(cudaMemcpyAsync(nwarn, d_w, b_w, cudaMemcpyDeviceToHost, st));
+  CKF(cudaStreamSynchronize(st));
+  return done(0);
+#undef CKF
+}
+
+int64_t mistra_bins_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

@@ -49,6 +49,12 @@ int fail(int code, const std::string &msg)
   g_err = msg;
   return code;
 }
+}  // namespace
+
+// shared with the other translation units of the library (bins_kernels.cu)
+int mistra_internal_fail(int code, const std::string &msg) { return fail(code, msg); }
+
+namespace {
 
 int cuda_fail(cudaError_t e, const char *what)
 {
