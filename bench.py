@@ -467,7 +467,7 @@ def run_bins_leg(args, dev, world, rank, barrier):
     bytes_snap = n * tile
     res = {"metric": "bin_redistribution_layers_per_s", "value": n * world / (ms * 1e-3), "unit": "layers/s",
            "layers_per_gpu": n, "ms_per_step": ms, "gpu_launches": int(launches),
-           "workload": "synthetic 70x70 particle spectra, 4 chem bins, +-5 % ion mass change per bin "
+           "workload": "synthetic 70x70 particle spectra, 4 chem bins, +-5 %% ion mass change per bin "
                        "(%.1f GB of ff per GPU: larger than L2)" % (n * tile * 1e-9),
            "roofline": {"bound": "hbm", "kernel": "bins_redistribute_kernel",
                         "achieved": bytes_red / (ms_red * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -478,7 +478,7 @@ def run_bins_leg(args, dev, world, rank, barrier):
                                      "achieved": bytes_snap / (ms_snap * 1e-3) * 1e-9,
                                      "frac": bytes_snap / (ms_snap * 1e-3) * 1e-9 / peaks["hbm_gbs"]}}}
     if not args.no_e2e:
-        h = {k: np.ascontiguousarray(v) for k, v in d.items()}
+        h = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in d.items()}
         t0 = time.perf_counter()
         reps = max(1, min(args.steps, 3))
         for _ in range(reps):

@@ -24,9 +24,14 @@
  *   sl1    [ncell][4][121]    = sl1(j2,nkc,k)   COMMON /blck17/   in/out
  *   sap, smp [ncell][4], sion1o [ncell][4][9]   locals of stem_kpp carried between the calls
  *   nwarn  [ncell] or NULL    number of "aerosol growth" messages (x0 <= 0, str.f90:6027)
- * Results: ff, sap, smp bit-identical to the reference's loop order; the transferred
- * volumes vc are summed per water bin first (a parallel reduction), so sl1/sion1 agree
- * to rounding (<= 1e-13 relative), not to the bit.
+ * Numerics: every statement is evaluated in binary64 with the reference's operation
+ * order (no FMA contraction), with two documented reassociations: (1) the particle
+ * number of a bin, sap, is summed per dry class first and then over classes - the
+ * reference keeps one running sum over all (ia, jt) (str.f90:5949), a 1600-long dependent
+ * chain; (2) the transferred volumes vc are summed per water bin first.  Hence sap agrees
+ * with the reference loop order to 1e-13, ff to 1e-11 and sl1/sion1 to 1e-11 relative
+ * (measured: a few 1e-16).  libmistra_kpp_strict.so (-DKPP_STRICT) keeps the running sum
+ * for sap and reproduces ff, sap, smp to the last bit; the tests check both.
  *
  * All functions return 0 or a negative MISTRA_KPP_E* code (mistra_kpp.h); the text is
  * available from mistra_kpp_last_error().  No CPU fallback.

@@ -84,8 +84,8 @@ def _grid_struct(g):
     return s, keep
 
 
-def _lib():
-    L = _kpp.library()
+def _lib(strict=False):
+    L = _kpp.library(strict)
     if not getattr(L, "_bins_ready", False):
         L.mistra_bins_launch_count.restype = C.c_int64
         L._bins_ready = True
@@ -100,9 +100,10 @@ def _vp(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def snapshot(g, ff, cm, sion1, sion1o=None):
-    """HOST numpy arrays.  Returns (sap[n,4], smp[n,4], sion1o[n,4,9])."""
-    L = _lib()
+def snapshot(g, ff, cm, sion1, sion1o=None, strict=False):
+    """HOST numpy arrays.  Returns (sap[n,4], smp[n,4], sion1o[n,4,9]).  strict=True uses the
+    -DKPP_STRICT build, which sums sap in the reference's running order (bit parity tests)."""
+    L = _lib(strict)
     gs, keep = _grid_struct(g)
     ff = np.ascontiguousarray(ff, dtype=np.float64)
     n = ff.shape[0]
@@ -116,9 +117,9 @@ def snapshot(g, ff, cm, sion1, sion1o=None):
     return sap, smp, so
 
 
-def redistribute(g, ff, cm, cw, sap, smp, sion1o, sion1, sl1):
+def redistribute(g, ff, cm, cw, sap, smp, sion1o, sion1, sl1, strict=False):
     """HOST numpy arrays (not modified).  Returns (ff, sion1, sl1, nwarn)."""
-    L = _lib()
+    L = _lib(strict)
     gs, keep = _grid_struct(g)
     ff = np.ascontiguousarray(ff, dtype=np.float64).copy()
     n = ff.shape[0]

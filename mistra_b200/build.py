@@ -102,6 +102,20 @@ def build(verbose=False, strict=True, ptxas_v=False):
     return outs
 
 
+def build_variant(tag, extra_flags, units=("kpp_mech_a.cu",), verbose=False):
+    """Experiment build: libmistra_kpp_<tag>.so = the product objects with `units` recompiled
+    with extra nvcc flags (e.g. -DKPP_MIN_BLOCKS=3).  Select it at run time with
+    MISTRA_KPP_LIB=libmistra_kpp_<tag>.so (mistra_b200/kpp.py)."""
+    objs = []
+    with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
+        jobs = [ex.submit(_compile, u, list(extra_flags) if u in units else [], tag if u in units else "fast", verbose)
+                for u in UNITS]
+        objs = [j.result() for j in jobs]
+    so = os.path.join(HERE, "libmistra_kpp_%s.so" % tag)
+    subprocess.check_call([NVCC] + ARCH + ["-shared", "-ccbin", HOSTCXX, "-cudart", "static", "-o", so] + objs)
+    return so
+
+
 def build_f77(verbose=False):
     """Boundary B1 shims (include/mistra_kpp_f77.h) over libmistra_kpp.so."""
     so = os.path.join(HERE, "libmistra_kpp_f77.so")
@@ -141,6 +155,18 @@ def build_rconst(verbose=False):
         f.write(hv)
     return so
 
+
+if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[1] == "--variant":
+    # python -m mistra_b200.build --variant mb3 -DKPP_MIN_BLOCKS=3 [--units kpp_mech_a.cu,kpp_mech_g.cu]
+    units = ("kpp_mech_a.cu",)
+    flags = []
+    for a in sys.argv[3:]:
+        if a.startswith("--units="):
+            units = tuple(a.split("=", 1)[1].split(","))
+        else:
+            flags.append(a)
+    print(build_variant(sys.argv[2], flags, units, verbose=True))
+    sys.exit(0)
 
 if __name__ == "__main__":
     print("\n".join(build(verbose=True, strict="--no-strict" not in sys.argv,

@@ -47,6 +47,50 @@ __device__ __forceinline__ void ia_range(const GridDev &g, int kc, int &ial, int
   else { ial = g.ka + 1; iau = g.nka - 1; }                   // str.f90:5932-5935
 }
 
+// Asynchronous global->shared tile copies (cp.async, LDGSTS in SASS): no registers, and
+// the copy overlaps the per-layer scalar work issued before tile_wait().
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)),
+               "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)),
+               "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void tile_wait()
+{
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+__device__ __forceinline__ void tile_load_async(double *__restrict__ dst, const double *__restrict__ src, int n)
+{
+  if ((n & 1) == 0)
+    for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) cp_async16(dst + 2 * i, src + 2 * i);
+  else
+    for (int i = threadIdx.x; i < n; i += blockDim.x) cp_async8(dst + i, src + i);
+}
+__device__ __forceinline__ void tile_load_padded_async(double *__restrict__ dst, const double *__restrict__ src,
+                                                       int n, int nkt, int TS)
+{
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r0 = i / nkt;
+    cp_async8(dst + r0 * TS + (i - r0 * nkt), src + i);
+  }
+}
+
+// Coalesced 16-byte write-back of a tile.
+__device__ __forceinline__ void tile_store(double *__restrict__ dst, const double *__restrict__ src, int n)
+{
+  if ((n & 1) == 0) {
+    const double2 *s2 = reinterpret_cast<const double2 *>(src);
+    double2 *d2 = reinterpret_cast<double2 *>(dst);
+    for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) d2[i] = s2[i];
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  }
+}
+
 // ---- str.f90:5916-5966 ---------------------------------------------------------------
 __global__ void __launch_bounds__(BINS_THREADS)
 bins_snapshot_kernel(GridDev g, long long ncell, const double *__restrict__ ff,
@@ -54,10 +98,10 @@ bins_snapshot_kernel(GridDev g, long long ncell, const double *__restrict__ ff,
                      double *__restrict__ sap, double *__restrict__ smp,
                      double *__restrict__ sion1o)
 {
-  extern __shared__ double sm[];
-  const int nka = g.nka, nkt = g.nkt, ntile = nka * nkt;
-  double *t_ff = sm;
-  double *s_en = sm + ntile;
+  extern __shared__ __align__(16) double sm[];
+  const int nka = g.nka, nkt = g.nkt, ntile = nka * nkt, TS = nkt | 1;
+  double *t_ff = sm;                         // [nka][TS]
+  double *s_en = sm + nka * TS;
   int *s_kw = (int *)(s_en + nka);
   for (int i = threadIdx.x; i < nka; i += blockDim.x) { s_en[i] = g.en[i]; s_kw[i] = g.kw[i]; }
   for (long long c = blockIdx.x; c < ncell; c += gridDim.x) {
@@ -65,8 +109,30 @@ bins_snapshot_kernel(GridDev g, long long ncell, const double *__restrict__ ff,
     for (int kc = 0; kc < g.nkc_l; ++kc) any |= (cm[c * NKC + kc] != 0.0);
     __syncthreads();  // previous tile fully consumed
     if (any) {
-      const double *f = ff + (size_t)c * ntile;
-      for (int i = threadIdx.x; i < ntile; i += blockDim.x) t_ff[i] = f[i];
+      tile_load_padded_async(t_ff, ff + (size_t)c * ntile, ntile, nkt, TS);
+      tile_wait();
+    }
+    __syncthreads();
+    // fs(ia,kc) = sum_jt ff*en is an independent chain per dry class: one thread per
+    // (kc parity, ia); the long chains (sap over all (ia,jt) of the bin, smp over ia) stay
+    // sequential in the reference's order on one thread per chem bin.
+    double *s_fs = (double *)(s_kw + nka + (nka & 1));   // [2][nka]: aerosol part / droplet part
+    double *s_ns = s_fs + 2 * nka;                       // [2][nka]: particle number per class
+    for (int p = threadIdx.x; p < 2 * nka; p += blockDim.x) {
+      const int part = p / nka, ia = p % nka + 1;
+      int jtl, jtu;
+      if (part == 0) { jtl = 1; jtu = s_kw[ia - 1]; }
+      else { jtl = s_kw[ia - 1] + 1; jtu = nkt; }
+      const double en = s_en[ia - 1];
+      const double *row = t_ff + (ia - 1) * TS;
+      double fs = 0.0, ns = 0.0;
+      for (int jt = jtl; jt <= jtu; ++jt) {
+        const double v = row[jt - 1];
+        fs = __dadd_rn(fs, __dmul_rn(v, en));        // str.f90:5948
+        ns = __dadd_rn(ns, v);
+      }
+      s_fs[p] = fs;
+      s_ns[p] = ns;
     }
     __syncthreads();
     const int kc = threadIdx.x + 1;
@@ -76,18 +142,19 @@ bins_snapshot_kernel(GridDev g, long long ncell, const double *__restrict__ ff,
         int ial, iau;
         ia_range(g, kc, ial, iau);
         for (int ia = ial; ia <= iau; ++ia) {
+#ifdef KPP_STRICT
+          // the reference's running sum over (ia, jt) (str.f90:5949), one rounding per particle bin
           int jtl, jtu;
           if (kc <= 2) { jtl = 1; jtu = s_kw[ia - 1]; }
           else { jtl = s_kw[ia - 1] + 1; jtu = nkt; }
-          const double en = s_en[ia - 1];
-          double fs = 0.0;
-          const double *row = t_ff + (ia - 1) * nkt;
-          for (int jt = jtl; jt <= jtu; ++jt) {
-            const double v = row[jt - 1];
-            fs = __dadd_rn(fs, __dmul_rn(v, en));  // str.f90:5948
-            sapk = __dadd_rn(sapk, v);             // str.f90:5949
-          }
-          smpk = __dadd_rn(smpk, fs);              // str.f90:5951
+          const double *row = t_ff + (ia - 1) * TS;
+          for (int jt = jtl; jt <= jtu; ++jt) sapk = __dadd_rn(sapk, row[jt - 1]);
+#else
+          // per-class partial sums first: the 1600-long dependent chain of FP64 adds
+          // (~45 cycles each) becomes 70 chains of <= 70 in parallel + one of <= 70
+          sapk = __dadd_rn(sapk, s_ns[(kc <= 2 ? 0 : nka) + ia - 1]);
+#endif
+          smpk = __dadd_rn(smpk, s_fs[(kc <= 2 ? 0 : nka) + ia - 1]);   // str.f90:5951
         }
         for (int l = 0; l < LSP; ++l)              // str.f90:5959-5962
           sion1o[(c * NKC + kc - 1) * LSP + l] = sion1[(c * NKC + kc - 1) * J6 + c_lj2[l] - 1];
@@ -106,7 +173,7 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
                          const double *__restrict__ sion1o, double *__restrict__ sion1,
                          double *__restrict__ sl1, int *__restrict__ nwarn)
 {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int nka = g.nka, nkt = g.nkt, ntile = nka * nkt;
   double *t_ff = sm;                         // [nka][nkt]
   double *s_en = t_ff + ntile;               // [nka]
@@ -114,7 +181,9 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
   double *s_vcp = s_c0 + NKC * nka;          // [NKC*NKC][nkt] per-jt partial volumes
   double *s_vc = s_vcp + NKC * NKC * nkt;    // [NKC*NKC]
   double *s_den = s_vc + NKC * NKC;          // [NKC]
-  int *s_kw = (int *)(s_den + NKC);          // [nka]
+  double *s_ds = s_den + NKC;                // [NKC][LSP]
+  double *s_c1 = s_ds + NKC * LSP;           // [NKC][nka]  1 - c0
+  int *s_kw = (int *)(s_c1 + NKC * nka);     // [nka]
   int *s_ix = s_kw + nka;                    // [NKC][nka]
   int *s_act = s_ix + NKC * nka;             // [NKC] + warn counter
   const double fpi = 4.0 / 3.0 * 3.1415926535897932;  // str.f90:5838
@@ -123,24 +192,33 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
 
   for (long long c = blockIdx.x; c < ncell; c += gridDim.x) {
     __syncthreads();
+    bool any = false;
+    for (int kc = 0; kc < g.nkc_l; ++kc) any |= (cm[c * NKC + kc] != 0.0 && sap[c * NKC + kc] > 1.e-6);
+    double *f = ff + (size_t)c * ntile;
+    if (any) tile_load_async(t_ff, f, ntile);    // in flight during phases 0 and 1
     // ---- phase 0: mass change per particle of every bin (str.f90:5979-5993) ----
+    if (threadIdx.x < NKC * LSP) {           // the 36 ion differences in parallel
+      const int kc = threadIdx.x / LSP + 1, l = threadIdx.x % LSP;
+      double v = 0.0;
+      if (kc <= g.nkc_l && cm[c * NKC + kc - 1] != 0.0 && sap[c * NKC + kc - 1] > 1.e-6) {
+        const double d = __dadd_rn(sion1[(c * NKC + kc - 1) * J6 + c_lj2[l] - 1],
+                                   -sion1o[(c * NKC + kc - 1) * LSP + l]);
+        v = __ddiv_rn(__dmul_rn(d, em6), sap[c * NKC + kc - 1]);
+      }
+      s_ds[threadIdx.x] = v;
+    }
+    __syncthreads();
     if (threadIdx.x < NKC) {
       const int kc = threadIdx.x + 1;
       int act = 0;
       double den = 0.0;
       if (kc <= g.nkc_l && cm[c * NKC + kc - 1] != 0.0 && sap[c * NKC + kc - 1] > 1.e-6) {
         act = 1;
-        const double sapk = sap[c * NKC + kc - 1];
-        double ds[LSP];
-        for (int l = 0; l < LSP; ++l) {
-          const double d = __dadd_rn(sion1[(c * NKC + kc - 1) * J6 + c_lj2[l] - 1],
-                                     -sion1o[(c * NKC + kc - 1) * LSP + l]);
-          ds[l] = __ddiv_rn(__dmul_rn(d, em6), sapk);
-        }
         const double mw[LSP] = {1., 18., 96., 44., 62., 35.5, 97., 23., 95.};
-        double s = __dmul_rn(ds[0], mw[0]);
-        for (int l = 1; l < LSP; ++l) s = __dadd_rn(s, __dmul_rn(ds[l], mw[l]));
-        den = __dmul_rn(s, 1000.);
+        const double *ds = s_ds + (kc - 1) * LSP;
+        double sacc = __dmul_rn(ds[0], mw[0]);
+        for (int l = 1; l < LSP; ++l) sacc = __dadd_rn(sacc, __dmul_rn(ds[l], mw[l]));
+        den = __dmul_rn(sacc, 1000.);
       }
       s_act[threadIdx.x] = act;
       s_den[threadIdx.x] = den;
@@ -148,10 +226,7 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
     if (threadIdx.x == NKC) s_act[NKC] = 0;  // warn counter
     for (int i = threadIdx.x; i < NKC * NKC * nkt; i += blockDim.x) s_vcp[i] = 0.0;
     __syncthreads();
-    const bool any = s_act[0] | s_act[1] | s_act[2] | s_act[3];
     if (any) {
-      double *f = ff + (size_t)c * ntile;
-      for (int i = threadIdx.x; i < ntile; i += blockDim.x) t_ff[i] = f[i];
       // ---- phase 1: target class ix and split c0 of every (kc, ia) (str.f90:6023-6044) ----
       for (int p = threadIdx.x; p < NKC * nka; p += blockDim.x) {
         const int kc = p / nka + 1, ia = p % nka + 1;
@@ -165,12 +240,16 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
             const double x0 = __dadd_rn(en, __dmul_rn(__ddiv_rn(__dmul_rn(den, en), smp[c * NKC + kc - 1]),
                                                       sap[c * NKC + kc - 1]));
             if (!(den > 0.0) && x0 <= 0.0) atomicAdd(&s_act[NKC], 1);
-            for (int iia = 1; iia <= nka - 1; ++iia) {
-              if (s_en[iia - 1] <= x0 && s_en[iia] > x0) {
-                ix = iia;
-                c0 = __ddiv_rn(__dadd_rn(s_en[iia], -x0), __dadd_rn(s_en[iia], -s_en[iia - 1]));
-                break;
+            // en is strictly increasing, so the reference's linear scan for
+            // en(iia) <= x0 < en(iia+1) has at most one hit: bisect for it
+            if (x0 >= s_en[0] && x0 < s_en[nka - 1]) {
+              int lo = 1, hi = nka;                  // invariant: en(lo) <= x0 < en(hi)
+              while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_en[mid - 1] <= x0) lo = mid; else hi = mid;
               }
+              ix = lo;
+              c0 = __ddiv_rn(__dadd_rn(s_en[lo], -x0), __dadd_rn(s_en[lo], -s_en[lo - 1]));
             }
             if (ix == 0) {
               if (s_en[0] > x0) { ix = 1; c0 = 1.0; }
@@ -180,7 +259,9 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
         }
         s_ix[p] = ix;
         s_c0[p] = c0;
+        s_c1[p] = __dadd_rn(1.0, -c0);
       }
+      tile_wait();
       __syncthreads();
       // ---- phase 2: one thread per water bin jt walks the dry classes (str.f90:6012-6096) ----
       const int jt = threadIdx.x + 1;
@@ -199,7 +280,7 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
             if (x1 > 0.0) {
               const int ix = s_ix[(kc - 1) * nka + ia - 1];
               const double c0 = s_c0[(kc - 1) * nka + ia - 1];
-              const double a = __dmul_rn(x1, c0), b = __dmul_rn(x1, __dadd_rn(1.0, -c0));
+              const double a = __dmul_rn(x1, c0), b = __dmul_rn(x1, s_c1[(kc - 1) * nka + ia - 1]);
               t_ff[(ia - 1) * nkt + jt - 1] = 0.0;
               t_ff[(ix - 1) * nkt + jt - 1] = __dadd_rn(t_ff[(ix - 1) * nkt + jt - 1], a);
               t_ff[ix * nkt + jt - 1] = __dadd_rn(t_ff[ix * nkt + jt - 1], b);
@@ -208,8 +289,11 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
               else tix = (jt > s_kw[ix - 1]) ? 3 : 1;
               if (ix + 1 > g.ka) tixp = (jt > s_kw[ix]) ? 4 : 2;
               else tixp = (jt > s_kw[ix]) ? 3 : 1;
-              const double r = g.rq[(ia - 1) * nkt + jt - 1];
-              const double r3 = __dmul_rn(__dmul_rn(r, r), r);
+              double r3 = 0.0;
+              if (tix != kc || tixp != kc) {        // rare: the move crosses a chem-bin limit
+                const double r = g.rq[(ia - 1) * nkt + jt - 1];
+                r3 = __dmul_rn(__dmul_rn(r, r), r);
+              }
               if (tix != kc) {
                 double *v = &s_vcp[((kc - 1) * NKC + tix - 1) * nkt + jt - 1];
                 *v = __dadd_rn(*v, __dmul_rn(__dmul_rn(a, fpi), r3));
@@ -229,7 +313,7 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
         for (int j = 0; j < nkt; ++j) s = __dadd_rn(s, s_vcp[threadIdx.x * nkt + j]);
         s_vc[threadIdx.x] = s;
       }
-      for (int i = threadIdx.x; i < ntile; i += blockDim.x) f[i] = t_ff[i];
+      tile_store(f, t_ff, ntile);
       __syncthreads();
       // ---- phase 4: exchange of dissolved species between bins (str.f90:6102-6134) ----
       for (int pass = 0; pass < 2; ++pass) {
@@ -347,14 +431,35 @@ int grid_to_device(const mistra_bins_grid *g, cudaStream_t st, GridDev *out, Gri
   return 0;
 }
 
+// device staging of the host-buffer entries, grown on demand and kept
+struct Scratch { char *p = nullptr; size_t bytes = 0; };
+Scratch g_scratch[16];
+
+int scratch(size_t bytes, char **out)
+{
+  int dev = -1;
+  CKB(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return mistra_internal_fail(MISTRA_KPP_ENODEVICE, "device index out of range");
+  Scratch &sc = g_scratch[dev];
+  if (sc.bytes < bytes) {
+    if (sc.p) { CKB(cudaDeviceSynchronize()); cudaFree(sc.p); sc.p = nullptr; sc.bytes = 0; }
+    CKB(cudaMalloc(&sc.p, bytes));
+    sc.bytes = bytes;
+  }
+  *out = sc.p;
+  return 0;
+}
+
+size_t tile_stride(int nkt) { return (size_t)(nkt | 1); }
+
 size_t smem_snapshot(const mistra_bins_grid *g)
 {
-  return sizeof(double) * ((size_t)g->nka * g->nkt + g->nka) + sizeof(int) * g->nka;
+  return sizeof(double) * ((size_t)g->nka * tile_stride(g->nkt) + g->nka + 4 * g->nka) + sizeof(int) * (g->nka + 2);
 }
 size_t smem_redistribute(const mistra_bins_grid *g)
 {
   const size_t nka = g->nka, nkt = g->nkt;
-  return sizeof(double) * (nka * nkt + nka + NKC * nka + NKC * NKC * nkt + NKC * NKC + NKC) +
+  return sizeof(double) * (nka * nkt + nka + 2 * NKC * nka + NKC * NKC * nkt + NKC * NKC + NKC + NKC * LSP) +
          sizeof(int) * (nka + NKC * nka + NKC + 4);
 }
 
@@ -432,10 +537,10 @@ int mistra_bins_snapshot(const mistra_bins_grid *g, int64_t ncell, const double 
   const size_t n = (size_t)ncell, tile = (size_t)g->nka * g->nkt;
   const size_t b_ff = n * tile * 8, b_c = n * NKC * 8, b_si = n * NKC * J6 * 8, b_so = n * NKC * LSP * 8;
   char *d = nullptr;
-  CKB(cudaMalloc(&d, b_ff + 3 * b_c + b_si + b_so));
+  if ((rc = scratch(b_ff + 3 * b_c + b_si + b_so, &d))) return rc;
   double *d_ff = (double *)d, *d_cm = (double *)(d + b_ff), *d_sap = d_cm + n * NKC, *d_smp = d_sap + n * NKC;
   double *d_si = d_smp + n * NKC, *d_so = (double *)((char *)d_si + b_si);
-  auto done = [&](int r) { cudaFree(d); return r; };
+  auto done = [&](int r) { return r; };
 #define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(mistra_internal_fail(MISTRA_KPP_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
   CKF(cudaMemcpyAsync(d_ff, ff, b_ff, cudaMemcpyHostToDevice, st));
   CKF(cudaMemcpyAsync(d_cm, cm, b_c, cudaMemcpyHostToDevice, st));
@@ -465,12 +570,12 @@ int mistra_bins_redistribute(const mistra_bins_grid *g, int64_t ncell, double *f
   const size_t b_ff = n * tile * 8, b_c = n * NKC * 8, b_si = n * NKC * J6 * 8, b_so = n * NKC * LSP * 8,
                b_sl = n * NKC * J2 * 8, b_w = n * 4;
   char *d = nullptr;
-  CKB(cudaMalloc(&d, b_ff + 4 * b_c + b_si + b_so + b_sl + b_w));
+  if ((rc = scratch(b_ff + 4 * b_c + b_si + b_so + b_sl + b_w, &d))) return rc;
   double *d_ff = (double *)d, *d_cm = (double *)(d + b_ff), *d_cw = d_cm + n * NKC, *d_sap = d_cw + n * NKC,
          *d_smp = d_sap + n * NKC;
   double *d_si = d_smp + n * NKC, *d_so = (double *)((char *)d_si + b_si), *d_sl = (double *)((char *)d_so + b_so);
   int32_t *d_w = (int32_t *)((char *)d_sl + b_sl);
-  auto done = [&](int r) { cudaFree(d); return r; };
+  auto done = [&](int r) { return r; };
   CKF(cudaMemcpyAsync(d_ff, ff, b_ff, cudaMemcpyHostToDevice, st));
   CKF(cudaMemcpyAsync(d_cm, cm, b_c, cudaMemcpyHostToDevice, st));
   CKF(cudaMemcpyAsync(d_cw, cw, b_c, cudaMemcpyHostToDevice, st));

@@ -42,7 +42,7 @@ _LIBS = {}
 
 def library(strict=False):
     """Load libmistra_kpp.so (or the -DKPP_STRICT -fmad=false test build)."""
-    name = "libmistra_kpp_strict.so" if strict else "libmistra_kpp.so"
+    name = "libmistra_kpp_strict.so" if strict else os.environ.get("MISTRA_KPP_LIB", "libmistra_kpp.so")
     if name not in _LIBS:
         so = os.path.join(_HERE, name)
         if not os.path.exists(so):

@@ -1,6 +1,9 @@
 """CUDA 2-D bin redistribution vs the CPU oracle through the C ABI (-m gpu).
-Contract (include/mistra_bins.h): ff, sap, smp, sion1o bit-identical; sl1/sion1 after the
-bin exchange to 1e-12 relative (the transferred volume is a parallel sum over water bins)."""
+Contract (include/mistra_bins.h): the product build sums the particle number of a bin per
+dry class first (a reassociation of the reference's running sum), so sap agrees to 1e-13
+and ff to 1e-11 relative; the -DKPP_STRICT build keeps the running sum and must reproduce
+ff, sap, smp, sion1o to the last bit.  sl1/sion1 after the bin exchange: 1e-12 relative in
+both (the transferred volume is reduced over water bins in parallel)."""
 import os
 
 import numpy as np
@@ -13,27 +16,42 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bins_layers.npz")
 
 
+def close(a, b, rtol):
+    return np.allclose(a, b, rtol=rtol, atol=1e-13 * max(np.abs(b).max(), 1e-300))
+
+
 def run_both(grid, d, sion1_new=None):
     new = d["sion1_new"] if sion1_new is None else sion1_new
     sap_o, smp_o, so_o = bo.snapshot(grid, d["ff"], d["cm"], d["sion1"])
-    sap, smp, so = bins.snapshot(grid, d["ff"], d["cm"], d["sion1"])
-    assert np.array_equal(sap, sap_o) and np.array_equal(smp, smp_o) and np.array_equal(so, so_o)
     ref = bo.redistribute(grid, d["ff"], d["cm"], d["cw"], sap_o, smp_o, so_o, new, d["sl1"])
+    # strict build: to the last bit
+    sap, smp, so = bins.snapshot(grid, d["ff"], d["cm"], d["sion1"], strict=True)
+    assert np.array_equal(sap, sap_o) and np.array_equal(smp, smp_o) and np.array_equal(so, so_o)
+    out = bins.redistribute(grid, d["ff"], d["cm"], d["cw"], sap, smp, so, new, d["sl1"], strict=True)
+    assert np.array_equal(out[0], ref[0]) and np.array_equal(out[3], ref[3])
+    assert close(out[1], ref[1], 1e-12) and close(out[2], ref[2], 1e-12)
+    # product build: reassociated particle-number sum
+    sap, smp, so = bins.snapshot(grid, d["ff"], d["cm"], d["sion1"])
+    assert np.allclose(sap, sap_o, rtol=1e-13, atol=0) and np.array_equal(smp, smp_o) and np.array_equal(so, so_o)
     out = bins.redistribute(grid, d["ff"], d["cm"], d["cw"], sap, smp, so, new, d["sl1"])
-    assert np.array_equal(out[0], ref[0])                                   # ff: to the last bit
-    assert np.allclose(out[1], ref[1], rtol=1e-12, atol=0) and np.allclose(out[2], ref[2], rtol=1e-12, atol=0)
-    assert np.array_equal(out[3], ref[3])
+    assert close(out[0], ref[0], 1e-11) and np.array_equal(out[3], ref[3])
+    assert close(out[1], ref[1], 1e-11) and close(out[2], ref[2], 1e-11)
     return out, ref
 
 
 def test_golden_layers(cuda_device, kpp):
     g = np.load(GOLD)
     grid = bins.particle_grid(*g["grid_args"])
-    sap, smp, so = bins.snapshot(grid, g["ff"], g["cm"], g["sion1"])
-    assert np.array_equal(sap, g["sap"]) and np.array_equal(smp, g["smp"]) and np.array_equal(so, g["sion1o"])
-    ff2, si2, sl2, nw = bins.redistribute(grid, g["ff"], g["cm"], g["cw"], sap, smp, so, g["sion1_new"], g["sl1"])
-    assert np.array_equal(ff2, g["ff_out"]) and np.array_equal(nw, g["nwarn"])
-    assert np.allclose(si2, g["sion1_out"], rtol=1e-12, atol=0) and np.allclose(sl2, g["sl1_out"], rtol=1e-12, atol=0)
+    for strict in (True, False):
+        sap, smp, so = bins.snapshot(grid, g["ff"], g["cm"], g["sion1"], strict=strict)
+        assert np.allclose(sap, g["sap"], rtol=1e-13, atol=0) and np.array_equal(smp, g["smp"])
+        assert np.array_equal(so, g["sion1o"])
+        ff2, si2, sl2, nw = bins.redistribute(grid, g["ff"], g["cm"], g["cw"], sap, smp, so, g["sion1_new"],
+                                              g["sl1"], strict=strict)
+        if strict:
+            assert np.array_equal(sap, g["sap"]) and np.array_equal(ff2, g["ff_out"])
+        assert close(ff2, g["ff_out"], 1e-11) and np.array_equal(nw, g["nwarn"])
+        assert close(si2, g["sion1_out"], 1e-11) and close(sl2, g["sl1_out"], 1e-11)
 
 
 @pytest.mark.parametrize("nkc_l,ial_first", [(4, 1), (2, 1), (4, 2), (1, 1)])
