@@ -125,7 +125,7 @@ def build_ensemble(mech, cols, rank, spinup, use_gpu, chunk_cols=500):
     arrays of the aqueous mechanism are large).  Spin-up uses the CUDA path when a
     GPU is present (it is input preparation, not part of the timed region)."""
     from mistra_b200 import synthetic
-    cls = {"gas": synthetic.GasEnsemble, "aer": synthetic.AerEnsemble}.get(mech)
+    cls = {"gas": synthetic.GasEnsemble, "aer": synthetic.AerEnsemble, "tot": synthetic.TotEnsemble}.get(mech)
     if cls is None:
         raise SystemExit("bench: synthetic inputs for mechanism %r are not available yet" % mech)
     if use_gpu:
@@ -397,7 +397,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "synthetic ensemble of independent Mistra columns (SURVEY 8d), "
-                                   "%d columns per GPU (148 gas cells + 98 aer cells each), mechanisms: %s; Ros3 0->10 s, "
+                                   "%d columns per GPU (148 gas cells, 98 aer / tot cells per column), mechanisms: %s; Ros3 0->10 s, "
                                    "RTOL 1e-3 ATOL 1e-25 Hstart 1e-3" % (args.cols, "+".join(mechs)),
                        "cells_per_gpu": ncell_rank, "columns_per_gpu": args.cols,
                        "parallelism": "cells sharded by column over %d GPU(s), no data-path collective" % world,

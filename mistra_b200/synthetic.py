@@ -246,17 +246,20 @@ EQUIL = {"H2O": (1.0e-5, -6716., 1.0e9, None, True, False), "HO2": (1.6e5, None,
          "I2": (5.e9, None, 3.85e9, None, False, True), "HIO3": (1.57e4, None, 1.0e5, None, True, False)}
 
 
-class AerEnsemble:
-    """Per-cell inputs of the aer mechanism (gas + aqueous chemistry in aerosol bins
-    1 = sulfate, 2 = sea salt) for the layers below nf of `ncol` columns: 98 cells per
-    column (k = 2..99; kpp.f90:4381-4391 - layers k >= nf are always gas-only)."""
+class _AqueousEnsemble:
+    """Per-cell inputs of a mechanism with aqueous chemistry for the layers below nf of
+    `ncol` columns: 98 cells per column (k = 2..99; kpp.f90:4381-4391 - layers k >= nf
+    are always gas-only).  Bins 1/2 = deliquesced sulfate / sea-salt aerosol, bins 3/4
+    (tot only) = the droplets grown on them."""
 
     LAYERS = NF - 2
+    MECH = None      # (id, name, number of aqueous bins)
 
     def __init__(self, ncol, seed=SEED, halo=True, iod=True, f32_literals=1, col0=0):
         g = GasEnsemble(ncol, seed=seed, halo=halo, iod=iod, f32_literals=f32_literals, col0=col0)
-        self.mech = 1
-        m = self.m = mechmod.load("aer")
+        self.mech, mname, nb = self.MECH
+        self.nbins = nb
+        m = self.m = mechmod.load(mname)
         self.f32 = f32_literals
         nspec = m.nvar + m.nfix
         idx = self.idx = {n: i for i, n in enumerate(m.spc_names)}
@@ -269,22 +272,24 @@ class AerEnsemble:
         tt, pk = self.cb1[:, 1], self.cb1[:, 3]
         f32 = (lambda x: float(np.float32(x))) if f32_literals else float
         # liquid water and effective radius per bin
-        aq = np.empty((ncol, 6))
+        aq = np.empty((ncol, 12))
         for c in range(ncol):
-            aq[c] = np.random.default_rng([seed, col0 + c, 1]).uniform(0.0, 1.0, 6)
+            aq[c] = np.random.default_rng([seed, col0 + c, 1]).uniform(0.0, 1.0, 12)
         aq = np.repeat(aq, L, axis=0)
-        cw = np.stack([10.0 ** (-11.5 + aq[:, 0]), 10.0 ** (-10.5 + aq[:, 1])], axis=1)   # m3/m3
-        rr = np.stack([8.0e-8 * 5.0 ** aq[:, 2], 8.0e-7 * 5.0 ** aq[:, 3]], axis=1)       # m
+        cw = np.stack([10.0 ** (-11.5 + aq[:, 0]), 10.0 ** (-10.5 + aq[:, 1]),
+                       10.0 ** (-8.3 + aq[:, 6]), 10.0 ** (-8.3 + aq[:, 7])], axis=1)[:, :nb]     # m3/m3
+        rr = np.stack([8.0e-8 * 5.0 ** aq[:, 2], 8.0e-7 * 5.0 ** aq[:, 3],
+                       3.0e-6 * 3.0 ** aq[:, 8], 5.0e-6 * 3.0 ** aq[:, 9]], axis=1)[:, :nb]       # m
         cv2 = 1.0e-3 / cw                                                                # conv2
         self.ycw = cw
         scal = np.zeros((ncell, 13))
         scal[:, 0] = CONV1
         scal[:, 1] = 1.0 if halo else 0.0
         scal[:, 2] = 1.0 if iod else 0.0
-        scal[:, 5:7] = 1.0                      # xliq1 = xliq2 = 1 -> xhet1 = xhet2 = 0
-        scal[:, 9:11] = cv2
+        scal[:, 5:5 + nb] = 1.0                 # xliq = 1 -> xhet1 = xhet2 = 0
+        scal[:, 9:9 + nb] = cv2
         self.scal = scal
-        # inverse dimensionless Henry constants (henry_a)
+        # inverse dimensionless Henry constants (henry_a / henry_t)
         tfact = 1.0 / tt - 3.3540e-3
         fct = 0.0820577 * tt
         yhenry = np.zeros((ncell, nspec))
@@ -294,25 +299,25 @@ class AerEnsemble:
         for s, a0 in HENRY_CONST.items():
             if s in idx:
                 yhenry[:, idx[s]] = 1.0 / (a0 * fct)
-        # mass-transfer coefficients (fast_k_mt_a for one radius per bin)
+        # mass-transfer coefficients (fast_k_mt_a / _t for one radius per bin)
         freep = 2.28e-5 * tt / pk
-        yxkmt = np.zeros((ncell, 2, nspec))
+        yxkmt = np.zeros((ncell, nb, nspec))
         for s in LEX:
             if s not in idx:
                 continue
             vmean = np.sqrt(tt / MOLMASS.get(s, 5.0e-2)) * 4.60138
             x1 = 4.0 / (3.0 * ALPHA.get(s, 0.1))
-            for kc in range(2):
+            for kc in range(nb):
                 yxkmt[:, kc, idx[s]] = vmean / (rr[:, kc] * (rr[:, kc] / freep + x1))
-        # equilibrium rate coefficients (equil_co_a, activity coefficients = 1)
-        ykef = np.zeros((ncell, 2, nspec))
-        ykeb = np.zeros((ncell, 2, nspec))
+        # equilibrium rate coefficients (equil_co_a / _t, activity coefficients = 1)
+        ykef = np.zeros((ncell, nb, nspec))
+        ykeb = np.zeros((ncell, nb, nspec))
         tf2 = 1.0 / tt - 3.354e-3
         for s, (f0, fb, b0, bb, bcv, fcv) in EQUIL.items():
-            for kc in range(2):
-                name = s % (1,) if "%d" in s else s      # the reference indexes by the bin-1 name
-                if name not in idx:
-                    continue
+            name = s % (1,) if "%d" in s else s          # the reference indexes by the bin-1 name
+            if name not in idx:
+                continue
+            for kc in range(nb):
                 kf = f0 * (np.exp(fb * tf2) if fb is not None else 1.0)
                 kb = b0 * (np.exp(bb * tf2) if bb is not None else 1.0)
                 ykef[:, kc, idx[name]] = kf * (cv2[:, kc] if fcv else 1.0)
@@ -326,34 +331,49 @@ class AerEnsemble:
             self.yxkmtd[:, :, idx[s]] = g.yxkmtd[sel][:, :, gi[s]]
         self.yxeq[:, idx["HNO3"]] = g.yxeq[sel][:, gi["HNO3"]]
         self.ycwd = g.ycwd[sel]
-        # FIX = O2, H2O, N2, H2Ol1, H2Ol2 with FIX(H2Olz) = 55.55/cvvz (aer.f:197-206)
-        assert m.spc_names[m.nvar:] == ["O2", "H2O", "N2", "H2Ol1", "H2Ol2"]
+        # FIX = O2, H2O, N2, H2Ol1.. with FIX(H2Olz) = 55.55/cvvz (aer.f:197-206)
+        assert m.spc_names[m.nvar:] == ["O2", "H2O", "N2"] + ["H2Ol%d" % (k + 1) for k in range(nb)]
         gf = g.fix[sel]
         self.fix = np.concatenate([gf, f32(55.55) / cv2], axis=1)
         # VAR: gas phase from the gas ensemble (by name), ions per initc (kpp.f90:337-381)
         var = np.zeros((ncell, m.nvar))
+        aqs = tuple("l%d" % (k + 1) for k in range(4))
         for s, i in gi.items():
-            if i < g.m.nvar and s in idx and idx[s] < m.nvar and not s.endswith(("l1", "l2")):
+            if i < g.m.nvar and s in idx and idx[s] < m.nvar and not s.endswith(aqs):
                 var[:, idx[s]] = g.var[sel][:, i]
-        x0 = (2.0 + 4.0 * aq[:, 4:6]) * 1.0e3 * cw          # mol/m3(air): 2..6 mol/l of salt
+        # aerosol: 2..6 mol/l of salt; droplets: the same kind of salt diluted to 1e-4..1e-3 mol/l
+        molar = np.stack([2.0 + 4.0 * aq[:, 4], 2.0 + 4.0 * aq[:, 5],
+                          10.0 ** (-4.0 + aq[:, 10]), 10.0 ** (-4.0 + aq[:, 11])], axis=1)[:, :nb]
+        x0 = molar * 1.0e3 * cw                              # mol/m3(air)
         xi = 1.0 if iod else 0.0
-        for s, f in (("NH4pl1", 1.34), ("SO42ml1", 0.34), ("NO3ml1", 0.004), ("HSO4ml1", 0.656)):
-            var[:, idx[s]] = f * x0[:, 0]
         xso4, xhco3, xno3, xbr = 0.0485, 4.2e-3, 1.0e-7, 1.45e-3
         xim, xio3 = 7.4e-8 / 0.545 * xi, 2.64e-7 / 0.545 * xi
         xcl = 1.0 - (xso4 + xhco3 + xno3 + xbr + xim + xio3)
-        for s, f in (("SO42ml2", xso4), ("HCO3ml2", xhco3), ("NO3ml2", xno3), ("Clml2", xcl),
-                     ("Brml2", xbr), ("Iml2", xim), ("IO3ml2", xio3), ("DOMl2", 0.27 * xbr)):
-            var[:, idx[s]] = f * x0[:, 1]
+        sulf = (("NH4pl", 1.34), ("SO42ml", 0.34), ("NO3ml", 0.004), ("HSO4ml", 0.656))
+        salt = (("SO42ml", xso4), ("HCO3ml", xhco3), ("NO3ml", xno3), ("Clml", xcl), ("Brml", xbr),
+                ("Iml", xim), ("IO3ml", xio3), ("DOMl", 0.27 * xbr))
+        for kc in range(nb):
+            for s, f in (sulf if kc % 2 == 0 else salt):
+                var[:, idx["%s%d" % (s, kc + 1)]] = f * x0[:, kc]
         self.var = var
 
     def conc(self, var=None):
         return np.concatenate([self.var if var is None else var, self.fix], axis=1)
 
     def rconst(self, var=None, sl=slice(None)):
-        """Update_RCONST_a for the cells in `sl` at concentrations `var`."""
+        """Update_RCONST_a / _t for the cells in `sl` at concentrations `var`."""
         c = self.conc(var)[sl]
-        return rc.update_rconst(1, self.cb1[sl], self.scal[sl], self.ph_rat[sl], c,
+        return rc.update_rconst(self.mech, self.cb1[sl], self.scal[sl], self.ph_rat[sl], c,
                                 yhenry=self.yhenry[sl], yxkmt=self.yxkmt[sl], ykef=self.ykef[sl],
                                 ykeb=self.ykeb[sl], yxkmtd=self.yxkmtd[sl], yxeq=self.yxeq[sl],
                                 ycw=self.ycw[sl], ycwd=self.ycwd[sl], f32_literals=self.f32)
+
+
+class AerEnsemble(_AqueousEnsemble):
+    """aer mechanism: gas + aqueous chemistry in the aerosol bins 1, 2."""
+    MECH = (1, "aer", 2)
+
+
+class TotEnsemble(_AqueousEnsemble):
+    """tot mechanism: gas + aerosol bins 1, 2 + droplet bins 3, 4 (cloudy layers)."""
+    MECH = (2, "tot", 4)

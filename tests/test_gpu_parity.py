@@ -90,6 +90,17 @@ def test_aer_synthetic_ensemble_vs_oracle(cuda_device, kpp, oracle):
         var = np.maximum(ref, 0.0)
 
 
+def test_tot_synthetic_ensemble_vs_oracle(cuda_device, kpp, oracle):
+    ens = synthetic.TotEnsemble(1)                 # 98 cloudy cells, 4 aqueous bins
+    var = ens.var
+    for step in range(2):
+        rc = ens.rconst(var)
+        ref, ierr_o, stats_o, hexit_o, _ = oracle.integrate(2, rc, ens.fix, var, nthreads=8)
+        out, ierr, stats, hexit, _tx = kpp.integrate(2, rc, ens.fix, var)
+        compare(out, ref, stats, stats_o, ierr, ierr_o, hexit, hexit_o, locked_tol=1e-5, hexit_rtol=1e-4)
+        var = np.maximum(ref, 0.0)
+
+
 @pytest.mark.parametrize("mi,name", MECHS)
 def test_random_cells_vs_oracle(cuda_device, kpp, oracle, mi, name):
     n = {"gas": 300, "aer": 96, "tot": 40}[name]
