@@ -56,6 +56,11 @@ def particle_grid(rnw0=0.005, rnw1=15.0, rw0=0.005, rw1=150.0, nka=70, nkt=70, n
         ew[jt] = ew[jt - 1] * ax
         e[jt] = 0.5 * (ew[jt] + ew[jt - 1])
     rq = (e[None, :] * 1.0e-6 / x1 + (rn[:, None] * 1.0e-6) ** 3) ** x0 * 1.0e6       # [nka,nkt]
+    rw = (ew[None, :] * 1.0e-6 / x1 + (rn[:, None] * 1.0e-6) ** 3) ** x0 * 1.0e6      # [nka,nkt]
+    dew = np.empty(nkt)
+    dew[0] = ew[0] - ewmin
+    dew[1:] = ew[1:] - ew[:-1]
+    dlgew = math.log10(ewmax / ewmin) / nkt
     zradthres = 0.1 if chamber else 0.5
     ka = -1
     for ia in range(nka):
@@ -72,7 +77,8 @@ def particle_grid(rnw0=0.005, rnw1=15.0, rw0=0.005, rw1=150.0, nka=70, nkt=70, n
         if kw[ia] < 0:
             kw[ia] = nkt
     return {"nka": nka, "nkt": nkt, "ka": int(ka), "nkc_l": nkc_l, "ial_first": ial_first,
-            "kw": kw, "en": en, "e": e, "rn": rn, "rq": np.ascontiguousarray(rq)}
+            "kw": kw, "en": en, "e": e, "rn": rn, "rq": np.ascontiguousarray(rq),
+            "ew": ew, "dew": dew, "rw": np.ascontiguousarray(rw), "dlne": math.log(10.0) * dlgew}
 
 
 def _grid_struct(g):

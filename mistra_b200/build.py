@@ -29,7 +29,9 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", HOSTCXX]
 
 UNITS = ["kpp_mech_g.cu", "kpp_mech_a.cu", "kpp_mech_t.cu", "kpp_api.cu", "bins_kernels.cu",
-         "_gen/kpp_names.cpp"]
+         "kon_kernels.cu", "_gen/kpp_names.cpp"]
+# per-unit flags: the condensation kernel keeps the reference's unfused arithmetic
+UNIT_FLAGS = {"kon_kernels.cu": ["-fmad=false"]}
 
 
 def _hash(paths, extra):
@@ -46,6 +48,8 @@ def _deps(unit):
             os.path.join(ROOT, "include", "mistra_kpp.h")]
     if unit.startswith("bins_"):
         deps.append(os.path.join(ROOT, "include", "mistra_bins.h"))
+    if unit.startswith("kon_"):
+        deps.append(os.path.join(ROOT, "include", "mistra_kon.h"))
     if unit.startswith("kpp_mech_"):
         x = unit[len("kpp_mech_")]
         deps += [os.path.join(CSRC, "_gen", "mech_%s.cuh" % x), os.path.join(CSRC, "ros3_kernel.inc")]
@@ -56,6 +60,7 @@ def _compile(unit, flags, tag, verbose):
     os.makedirs(OBJ, exist_ok=True)
     obj = os.path.join(OBJ, "%s.%s.o" % (unit.replace("/", "_"), tag))
     stamp = obj + ".sha"
+    flags = list(flags) + [f for f in UNIT_FLAGS.get(unit, []) if f not in flags]
     hv = _hash(_deps(unit), (flags, NVCC))
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == hv:
         return obj

@@ -1,0 +1,471 @@
+// Condensation / evaporation on the 2-D particle grid (include/mistra_kon.h): CUDA kernel +
+// C-ABI entries.  Role in the reference: SUBROUTINE subkon (/root/reference/src/str.f90:
+// 4987-5204) with SUBROUTINE advec (5321-5516) and diff_wat_vap / therm_conduct_air / xl21 /
+// p21 (5210-5315, 7640-7693), for every humid layer at once.
+//
+// Mapping: one CTA per layer.  Five nka x nkt tiles live in shared memory for the whole
+// layer (196 kB for 70 x 70, one CTA per SM): the growth-rate coefficients cd, cr, sr (set
+// up once by all threads, 18-band radiative sum from the L2-resident qabs table), the
+// spectrum before the step falt (cp.async from HBM) and the advected spectrum ffk (written
+// back once).  Per secant iteration one thread per dry class ia advects its row along the
+// water-mass axis exactly as advec does (sequential in i, scatter into k_low/k_high), the
+// advection velocities u(k) are evaluated on the fly from cd, cr, sr; the liquid-water
+// change is summed per row, then over rows by one thread, which also runs the secant
+// update.  Compiled without FMA contraction (build.py) so that the arithmetic is the
+// reference's up to the CUDA exp/pow (<= 2 ulp) and the per-row summation of dwsum.
+#include "../../include/mistra_kon.h"
+#include "../../include/mistra_kpp.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+int mistra_internal_fail(int code, const std::string &msg);  // kpp_api.cu
+
+namespace {
+
+constexpr int MB = MISTRA_MB;
+constexpr int KON_THREADS = 128;
+constexpr int MAXK = 128;
+
+struct KonGridDev {
+  int nka, nkt;
+  double a0m, dlne;
+  const double *en, *rn, *b0m, *ew, *e, *dew, *rw, *qabs;
+};
+
+// constants.f90:48-83
+__device__ constexpr double kGasConst = 8.3144743, kMair = 28.96546e-3, kMwat = 18.01528e-3;
+__device__ constexpr double kCp = 1005.0, kRhow = 1000.0, kPi = 3.1415926535897932;
+
+__device__ __forceinline__ double xl21(double t) { return 3138708. + (-2339.4) * t; }                       // str.f90:7661
+__device__ __forceinline__ double p21(double t) { return 610.7 * exp(17.15 * (t - 273.15) / (t - 38.33)); } // str.f90:7691
+__device__ __forceinline__ double therm_conduct_air(double t) { return 4.39e-3 + 7.1e-5 * t; }              // str.f90:5313
+__device__ __forceinline__ double diff_wat_vap(double t, double p)                                          // str.f90:5255-5257
+{
+  const double cst2 = 0.211e-4 * 101325. / 53286.64010226011;  // cst*P0/T0**exponent, a compile-time constant there
+  return cst2 * pow(t, 1.94) / p;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)),
+               "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)),
+               "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+struct RowCoef {
+  const double *cd, *cr, *sr;  // this row's coefficients in shared memory
+  double fquer, dlne;
+  int nkt;
+  // c(jt) of str.f90:5167 and the upstream velocities u(jt) of str.f90:5170-5175, 1-based
+  __device__ __forceinline__ double c(int jt) const
+  {
+    return (cd[jt - 1] * (fquer - sr[jt - 1]) - cr[jt - 1]) / dlne;
+  }
+  __device__ __forceinline__ double u(int jt) const
+  {
+    if (jt == 1) return fmax(0.0, c(1));
+    if (jt == nkt) return fmin(0.0, c(nkt - 1));
+    const double a = c(jt), b = c(jt - 1);
+    return 0.5 * (a + fabs(a) + b - fabs(b));
+  }
+};
+
+// SUBROUTINE advec (str.f90:5321-5516) for one row: z = spectrum before (read only),
+// y = advected spectrum (zeroed here, then scattered into).  Returns 1 where the reference
+// aborts (target bin outside the grid).
+__device__ int advec_row(int nkt, double dt, const RowCoef &rc, const double *__restrict__ z,
+                         double *__restrict__ y)
+{
+  const double ymin = 1.e-32;
+  for (int i = 0; i < nkt; ++i) y[i] = 0.0;
+  int i0 = 1;
+  while (z[i0 - 1] < ymin) {
+    if (i0 == nkt) return 0;
+    i0 = i0 + 1;
+  }
+  int i1 = nkt;
+  while (z[i1 - 1] < ymin) i1 = i1 - 1;
+  for (int i = i0; i <= i1; ++i) {
+    const double zi = z[i - 1];
+    if (zi < ymin) continue;
+    int k2 = 0, k1, k = i;
+    double dt0, dt1 = dt, x0;
+    double uk = rc.u(k);
+    if (fabs(uk) > 0.0) dt0 = fmin(1.0 / fabs(uk), dt1);
+    else { y[k - 1] = y[k - 1] + zi; continue; }
+    x0 = (double)k + uk * dt0;
+    dt1 = dt1 - dt0;
+    k1 = k;
+    bool done = false;
+    while (dt1 > 1.e-7) {
+      if (uk < 0.0) k = k - 1; else k = k + 1;
+      if (k == k2) { y[k - 1] = y[k - 1] + zi; done = true; break; }
+      k2 = k1;
+      k1 = k;
+      if (k < 1 || k > nkt) return 1;
+      uk = rc.u(k);
+      if (fabs(uk) > 0.0) dt0 = fmin(1.0 / fabs(uk), dt1);
+      else { y[k - 1] = y[k - 1] + zi; done = true; break; }
+      x0 = (double)k + uk * dt0;
+      dt1 = dt1 - dt0;
+    }
+    if (done) continue;
+    const int k_low = (int)floor(x0), k_high = k_low + 1;
+    const double c0 = x0 - (double)k_low;
+    if (k_low < 1 || (k_high > nkt && c0 > 0.0)) return 1;
+    if (c0 > 0.0) {
+      double x1;
+      if (i == 1 || i == nkt) {
+        x1 = c0 * zi;
+      } else if (i == 2 || i == nkt - 1) {
+        const double al = 1.0 - 2.0 * c0, al2 = al * al;
+        const double a0 = (26.0 * zi - z[i] - z[i - 2]) / 24.0;
+        const double a1 = (z[i] - z[i - 2]) / 16.0;
+        const double a2 = (z[i] + z[i - 2] - 2.0 * zi) / 48.0;
+        x1 = fmin(zi, a0 * c0 + a1 * (1.0 - al2) + a2 * (1.0 - al2 * al));
+      } else {
+        const double al = 1.0 - 2.0 * c0, al2 = al * al, al3 = al2 * al;
+        const double zp2 = z[i + 1], zp1 = z[i], zm1 = z[i - 2], zm2 = z[i - 3];
+        const double a0 = (9.0 * (zp2 + zm2) - 116.0 * (zp1 + zm1) + 2134.0 * zi) / 1920.0;
+        const double a1 = (-5.0 * (zp2 - zm2) + 34.0 * (zp1 - zm1)) / 384.0;
+        const double a2 = (-zp2 + 12.0 * (zp1 + zm1) - 22.0 * zi - zm2) / 384.0;
+        const double a3 = (zp2 - 2.0 * (zp1 - zm1) - zm2) / 768.0;
+        const double a4 = (zp2 - 4.0 * (zp1 + zm1) + 6.0 * zi + zm2) / 3840.0;
+        x1 = fmin(zi, a0 * c0 + a1 * (1.0 - al2) + a2 * (1.0 - al3) + a3 * (1.0 - al2 * al2)
+                          + a4 * (1.0 - al2 * al3));
+      }
+      x1 = fmax(0.0, x1);
+      y[k_low - 1] = y[k_low - 1] + zi - x1;
+      y[k_high - 1] = y[k_high - 1] + x1;
+    } else {
+      y[k_low - 1] = y[k_low - 1] + zi;
+    }
+  }
+  return 0;
+}
+
+__global__ void __launch_bounds__(KON_THREADS)
+kon_subkon_kernel(KonGridDev g, long long ncell, double dt, double *__restrict__ ffk_all,
+                  const double *__restrict__ totr_all, const double *__restrict__ dfdt_a,
+                  const double *__restrict__ feualt_a, const double *__restrict__ pp_a,
+                  double *__restrict__ to_a, const double *__restrict__ tn_a,
+                  double *__restrict__ xm1o_a, const double *__restrict__ xm1n_a,
+                  const int *__restrict__ kr_a, int *__restrict__ status)
+{
+  extern __shared__ __align__(16) double sm[];
+  const int nka = g.nka, nkt = g.nkt, ntile = nka * nkt;
+  double *s_cd = sm, *s_cr = s_cd + ntile, *s_sr = s_cr + ntile, *s_falt = s_sr + ntile, *s_ffk = s_falt + ntile;
+  double *s_dw = s_ffk + ntile;      // [nka] liquid-water change per dry class
+  double *s_e = s_dw + nka;          // [nkt]
+  double *s_totr = s_e + nkt;        // [MB]
+  double *s_it = s_totr + MB;        // [2] fquer, spare
+  int *s_flag = (int *)(s_it + 2);   // [0] stop code, [1] advec error, [2..2+nka) kr0 switch per class
+  const double r0 = kGasConst / kMair, r1 = kGasConst / kMwat;
+
+  for (int i = threadIdx.x; i < nkt; i += blockDim.x) s_e[i] = g.e[i];
+  // the reference lowers kr0 from 3 to 2 at the first class with rn < 0.5 and never
+  // restores it (str.f90:5141): a prefix flag over ia
+  if (threadIdx.x == 0) {
+    int seen = 0;
+    for (int ia = 0; ia < nka; ++ia) { seen |= (g.rn[ia] < 0.5); s_flag[2 + ia] = seen; }
+  }
+
+  for (long long c = blockIdx.x; c < ncell; c += gridDim.x) {
+    __syncthreads();
+    double *ffk = ffk_all + (size_t)c * ntile;
+    if ((ntile & 1) == 0)
+      for (int i = threadIdx.x; i < (ntile >> 1); i += blockDim.x) cp_async16(s_falt + 2 * i, ffk + 2 * i);
+    else
+      for (int i = threadIdx.x; i < ntile; i += blockDim.x) cp_async8(s_falt + i, ffk + i);
+    if (threadIdx.x < MB) s_totr[threadIdx.x] = totr_all[c * MB + threadIdx.x];
+    // ---- layer scalars (str.f90:5104-5127), by every thread ----
+    const double to0 = to_a[c], xm1o0 = xm1o_a[c], tn = tn_a[c], xm1n = xm1n_a[c], pp = pp_a[c];
+    const double feualt = feualt_a[c];
+    const double zxl21 = xl21(to0);
+    const double xldcp = zxl21 / kCp;
+    const double xka = therm_conduct_air(to0);
+    const double xdv = diff_wat_vap(to0, pp);
+    const double xl = 24.483 * to0 / pp;
+    const double deltav = 1.3 * xl, deltat = 2.7 * xl;
+    const double rho = pp / (r0 * to0 * (1.0 + 0.61 * xm1o0));
+    const double rho21 = p21(to0) / (r1 * to0);
+    const double rho21s = (zxl21 / (r1 * to0) - 1.0) * rho21 / to0;
+    const double a0 = g.a0m / to0;
+    const double xdv0 = xdv * sqrt(2.0 * kPi / (r1 * to0)) / 3.6e-08;
+    const double xka0 = xka * sqrt(2.0 * kPi / (r0 * to0)) / (7.e-07 * rho * kCp);
+    const int kr = kr_a[c];
+    __syncthreads();  // s_totr visible
+    const int ib0 = (s_totr[0] < 1.0) ? 7 : 1;
+    // ---- growth-rate coefficients over the grid (str.f90:5128-5149) ----
+    for (int q = threadIdx.x; q < ntile; q += blockDim.x) {
+      const int ia = q / nkt + 1, jt = q - (ia - 1) * nkt + 1;
+      const int jtp = jt + 1 < nkt ? jt + 1 : nkt;
+      const double de0 = g.dew[jt - 1], dep = g.dew[jtp - 1], de0p = de0 + dep;
+      const double rk = g.rw[q];
+      const double srq = fmax(0.1, exp(a0 / rk - g.b0m[ia - 1] * g.en[ia - 1] / g.ew[jt - 1]));
+      const double xdvs = xdv / (rk / (rk + deltav) + xdv0 / rk);
+      const double xkas = xka / (rk / (rk + deltat) + xka0 / rk);
+      const double x1 = kRhow * (zxl21 + xkas / (xdvs * rho21s * srq));
+      const int kr0 = (kr == 3 && s_flag[2 + ia - 1]) ? 2 : kr;
+      const double *qa = g.qabs + ((size_t)(kr0 - 1) * nka + (ia - 1)) * nkt * MB;
+      double rad = 0.0;
+      for (int ib = ib0; ib <= MB; ++ib)
+        rad = rad + s_totr[ib - 1] * (qa[(jt - 1) * MB + ib - 1] * de0 + qa[(jtp - 1) * MB + ib - 1] * dep) / de0p;
+      s_sr[q] = srq;
+      s_cd[q] = 3.e12 * rho21 * xkas / (x1 * rk * rk * rho21s * srq);
+      s_cr[q] = rad * 7.5e5 / (rk * x1) - kRhow * 4190. * (tn - to0) / (dt * x1);
+    }
+    // ---- secant iteration on the mean saturation ratio (str.f90:5151-5201) ----
+    double feuneu = feualt + dfdt_a[c] * dt;
+    if (feualt < 0.95) feuneu = xm1n * pp / (p21(tn) * (.62198 + .37802 * xm1n));
+    double fquer = 0.5 * (feuneu + feualt);
+    double res = 0.0, fqa = 0.0, to = to0, xm1o = xm1o0;
+    const double aa0 = 1.0 / dt;
+    int st = -1;
+    if (threadIdx.x == 0) { s_flag[0] = 0; s_flag[1] = 0; }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int itk = 1; itk <= 10; ++itk) {
+      if (threadIdx.x < nka) {
+        const int r = threadIdx.x * nkt;
+        RowCoef rc{s_cd + r, s_cr + r, s_sr + r, fquer, g.dlne, nkt};
+        const int bad = advec_row(nkt, dt, rc, s_falt + r, s_ffk + r);
+        if (bad) s_flag[1] = 1;
+        double dw = 0.0;
+        for (int jt = 0; jt < nkt; ++jt) dw = dw + (s_ffk[r + jt] - s_falt[r + jt]) * s_e[jt];
+        s_dw[threadIdx.x] = dw;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int stop = 0;
+        if (s_flag[1]) { st = -2; stop = 1; }
+        else {
+          double dwsum = 0.0;
+          for (int ia = 0; ia < nka; ++ia) dwsum = dwsum + s_dw[ia];
+          const double dmsum = dwsum / rho;
+          const double dtsum = xldcp * dmsum;
+          xm1o = xm1n - dmsum;
+          to = tn + dtsum;
+          const double p1 = xm1o * pp / (0.62198 + 0.37802 * xm1o);
+          feuneu = p1 / p21(to);
+          const double resold = res;
+          res = feuneu + feualt - 2.0 * fquer;
+          if (fabs(res) < 1.e-6) { st = itk; stop = 1; }
+          else {
+            const double dres = res - resold;
+            double aa = aa0;
+            if (itk > 1 && fabs(dres) > 1.e-8) aa = (fqa - fquer) / dres;
+            fqa = fquer;
+            fquer = fquer + aa * res;
+          }
+        }
+        s_it[0] = fquer;
+        s_flag[0] = stop;
+      }
+      __syncthreads();
+      fquer = s_it[0];
+      if (s_flag[0]) break;
+    }
+    // ---- write back ----
+    if ((ntile & 1) == 0) {
+      const double2 *s2 = reinterpret_cast<const double2 *>(s_ffk);
+      double2 *d2 = reinterpret_cast<double2 *>(ffk);
+      for (int i = threadIdx.x; i < (ntile >> 1); i += blockDim.x) d2[i] = s2[i];
+    } else {
+      for (int i = threadIdx.x; i < ntile; i += blockDim.x) ffk[i] = s_ffk[i];
+    }
+    if (threadIdx.x == 0) {
+      to_a[c] = to;
+      xm1o_a[c] = xm1o;
+      if (status) status[c] = st;
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+std::mutex g_mu;
+std::atomic<long long> g_launches{0};
+
+struct GridCache {
+  bool valid = false, attr_set = false;
+  int nka = 0, nkt = 0, num_sm = 0;
+  std::vector<double> host;   // concatenated copy for change detection
+  double *d = nullptr;        // device copy, same concatenation
+  size_t cap = 0;
+};
+GridCache g_cache[16];
+struct Scratch { char *p = nullptr; size_t bytes = 0; };
+Scratch g_scratch[16];
+
+#define CKK(call)                                                                       \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return mistra_internal_fail(e_ == cudaErrorMemoryAllocation ? MISTRA_KPP_ENOMEM   \
+                                  : (e_ == cudaErrorNoDevice ? MISTRA_KPP_ENODEVICE     \
+                                                             : MISTRA_KPP_ECUDA),       \
+                                  std::string(#call) + ": " + cudaGetErrorString(e_));  \
+  } while (0)
+
+int check_grid(const mistra_kon_grid *g)
+{
+  if (!g || !g->en || !g->rn || !g->b0m || !g->ew || !g->e || !g->dew || !g->rw || !g->qabs)
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "null grid");
+  if (g->nka < 1 || g->nka > KON_THREADS || g->nkt < 5 || g->nkt > MAXK)
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "grid size out of range (nka <= 128, 5 <= nkt <= 128)");
+  if (!(g->dlne > 0.0)) return mistra_internal_fail(MISTRA_KPP_EINVAL, "dlne <= 0");
+  return 0;
+}
+
+size_t smem_bytes(const mistra_kon_grid *g)
+{
+  const size_t ntile = (size_t)g->nka * g->nkt;
+  return sizeof(double) * (5 * ntile + g->nka + g->nkt + MB + 2) + sizeof(int) * (2 + g->nka + 2);
+}
+
+int grid_to_device(const mistra_kon_grid *g, cudaStream_t st, KonGridDev *out, GridCache **cache)
+{
+  int dev = -1;
+  CKK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return mistra_internal_fail(MISTRA_KPP_ENODEVICE, "device index out of range");
+  GridCache &gc = g_cache[dev];
+  const size_t nka = g->nka, nkt = g->nkt;
+  const size_t n_all = 3 * nka + 3 * nkt + nka * nkt + (size_t)MISTRA_JPTAERRAD * nka * nkt * MB;
+  std::vector<double> h;
+  h.reserve(n_all);
+  auto put = [&](const double *p, size_t n) { h.insert(h.end(), p, p + n); };
+  put(g->en, nka); put(g->rn, nka); put(g->b0m, nka); put(g->ew, nkt); put(g->e, nkt); put(g->dew, nkt);
+  put(g->rw, nka * nkt); put(g->qabs, (size_t)MISTRA_JPTAERRAD * nka * nkt * MB);
+  const bool same = gc.valid && gc.nka == g->nka && gc.nkt == g->nkt && gc.host.size() == h.size() &&
+                    !memcmp(gc.host.data(), h.data(), sizeof(double) * h.size());
+  if (!same) {
+    if (!gc.num_sm) {
+      cudaDeviceProp p;
+      CKK(cudaGetDeviceProperties(&p, dev));
+      gc.num_sm = p.multiProcessorCount;
+    }
+    if (gc.valid) CKK(cudaDeviceSynchronize());
+    if (gc.cap < h.size()) {
+      if (gc.d) cudaFree(gc.d);
+      gc.d = nullptr;
+      CKK(cudaMalloc(&gc.d, sizeof(double) * h.size()));
+      gc.cap = h.size();
+    }
+    gc.host.swap(h);
+    gc.nka = g->nka;
+    gc.nkt = g->nkt;
+    CKK(cudaMemcpyAsync(gc.d, gc.host.data(), sizeof(double) * gc.host.size(), cudaMemcpyHostToDevice, st));
+    CKK(cudaStreamSynchronize(st));
+    gc.valid = true;
+  }
+  if (!gc.attr_set) {
+    CKK(cudaFuncSetAttribute(kon_subkon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    gc.attr_set = true;
+  }
+  const double *p = gc.d;
+  out->nka = g->nka; out->nkt = g->nkt; out->a0m = g->a0m; out->dlne = g->dlne;
+  out->en = p; p += nka; out->rn = p; p += nka; out->b0m = p; p += nka;
+  out->ew = p; p += nkt; out->e = p; p += nkt; out->dew = p; p += nkt;
+  out->rw = p; p += nka * nkt; out->qabs = p;
+  *cache = &gc;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mistra_kon_subkon_device(const mistra_kon_grid *g, int64_t ncell, double dt, double *d_ffk,
+                             const double *d_totr, const double *d_dfdt, const double *d_feualt,
+                             const double *d_pp, double *d_to, const double *d_tn,
+                             double *d_xm1o, const double *d_xm1n, const int32_t *d_kr,
+                             int32_t *d_status, void *stream)
+{
+  int rc = check_grid(g);
+  if (rc) return rc;
+  if (ncell < 0) return mistra_internal_fail(MISTRA_KPP_EINVAL, "ncell < 0");
+  if (!(dt > 0.0)) return mistra_internal_fail(MISTRA_KPP_EINVAL, "dt <= 0");
+  if (ncell == 0) return 0;
+  if (!d_ffk || !d_totr || !d_dfdt || !d_feualt || !d_pp || !d_to || !d_tn || !d_xm1o || !d_xm1n || !d_kr)
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "null array");
+  const size_t smem = smem_bytes(g);
+  if (smem > 227 * 1024) return mistra_internal_fail(MISTRA_KPP_EINVAL, "grid too large for shared memory");
+  std::lock_guard<std::mutex> lk(g_mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  KonGridDev gd;
+  GridCache *gc;
+  if ((rc = grid_to_device(g, st, &gd, &gc))) return rc;
+  int per_sm = (int)((227 * 1024) / smem);
+  if (per_sm < 1) per_sm = 1;
+  long long blocks = (long long)gc->num_sm * per_sm;
+  if (blocks > ncell) blocks = ncell;
+  kon_subkon_kernel<<<(int)blocks, KON_THREADS, smem, st>>>(gd, ncell, dt, d_ffk, d_totr, d_dfdt, d_feualt, d_pp,
+                                                           d_to, d_tn, d_xm1o, d_xm1n, d_kr, d_status);
+  CKK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mistra_kon_subkon(const mistra_kon_grid *g, int64_t ncell, double dt, double *ffk,
+                      const double *totr, const double *dfdt, const double *feualt,
+                      const double *pp, double *to, const double *tn, double *xm1o,
+                      const double *xm1n, const int32_t *kr, int32_t *status, void *stream)
+{
+  int rc = check_grid(g);
+  if (rc) return rc;
+  if (ncell < 0) return mistra_internal_fail(MISTRA_KPP_EINVAL, "ncell < 0");
+  if (ncell == 0) return 0;
+  if (!ffk || !totr || !dfdt || !feualt || !pp || !to || !tn || !xm1o || !xm1n || !kr)
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "null array");
+  int dev = -1;
+  CKK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return mistra_internal_fail(MISTRA_KPP_ENODEVICE, "device index out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)ncell, b_ff = n * g->nka * g->nkt * 8, b_tr = n * MB * 8, b_s = n * 8, b_i = n * 4;
+  const size_t total = b_ff + b_tr + 7 * b_s + 2 * b_i + 64;
+  Scratch &sc = g_scratch[dev];
+  if (sc.bytes < total) {
+    if (sc.p) { CKK(cudaDeviceSynchronize()); cudaFree(sc.p); sc.p = nullptr; sc.bytes = 0; }
+    CKK(cudaMalloc(&sc.p, total));
+    sc.bytes = total;
+  }
+  char *p = sc.p;
+  double *d_ff = (double *)p; p += b_ff;
+  double *d_tr = (double *)p; p += b_tr;
+  double *d_s[7];
+  for (auto &q : d_s) { q = (double *)p; p += b_s; }
+  int32_t *d_kr = (int32_t *)p; p += b_i;
+  int32_t *d_st = (int32_t *)p;
+  const double *hs[7] = {dfdt, feualt, pp, to, tn, xm1o, xm1n};
+  CKK(cudaMemcpyAsync(d_ff, ffk, b_ff, cudaMemcpyHostToDevice, st));
+  CKK(cudaMemcpyAsync(d_tr, totr, b_tr, cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < 7; ++i) CKK(cudaMemcpyAsync(d_s[i], hs[i], b_s, cudaMemcpyHostToDevice, st));
+  CKK(cudaMemcpyAsync(d_kr, kr, b_i, cudaMemcpyHostToDevice, st));
+  if ((rc = mistra_kon_subkon_device(g, ncell, dt, d_ff, d_tr, d_s[0], d_s[1], d_s[2], d_s[3], d_s[4], d_s[5],
+                                     d_s[6], d_kr, status ? d_st : nullptr, stream)))
+    return rc;
+  CKK(cudaMemcpyAsync(ffk, d_ff, b_ff, cudaMemcpyDeviceToHost, st));
+  CKK(cudaMemcpyAsync(to, d_s[3], b_s, cudaMemcpyDeviceToHost, st));
+  CKK(cudaMemcpyAsync(xm1o, d_s[5], b_s, cudaMemcpyDeviceToHost, st));
+  if (status) CKK(cudaMemcpyAsync(status, d_st, b_i, cudaMemcpyDeviceToHost, st));
+  CKK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int64_t mistra_kon_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"
