@@ -56,3 +56,67 @@ module mistra_kpp_mod
      end function mistra_kpp_finalize
   end interface
 end module mistra_kpp_mod
+
+! mistra_bins_mod / mistra_kon_mod - ISO_C_BINDING interfaces of include/mistra_bins.h and
+! include/mistra_kon.h (2-D particle-grid kernels).  The grid structs hold C pointers to the
+! host arrays of COMMON /cb50/, /blck06/, /cb44/, /cb49/ (c_loc of the Fortran arrays).
+module mistra_bins_mod
+  use, intrinsic :: iso_c_binding
+  implicit none
+  type, bind(C) :: mistra_bins_grid
+     integer(c_int32_t) :: nka, nkt, ka, nkc_l, ial_first, reserved
+     type(c_ptr) :: kw, en, rq          ! kw(nka) int32, en(nka), rq(nkt,nka)
+  end type mistra_bins_grid
+  interface
+     ! ff(nkt,nka,ncell), cm(nkc,ncell), sion1(j6,nkc,ncell) -> sap(nkc,ncell), smp(nkc,ncell), sion1o(9,nkc,ncell)
+     function mistra_bins_snapshot(g, ncell, ff, cm, sion1, sap, smp, sion1o, stream) result(rc) &
+          bind(C, name="mistra_bins_snapshot")
+       import :: c_int, c_int64_t, c_double, c_ptr, mistra_bins_grid
+       type(mistra_bins_grid), intent(in) :: g
+       integer(c_int64_t), value :: ncell
+       real(c_double), intent(in) :: ff(*), cm(*), sion1(*)
+       real(c_double), intent(out) :: sap(*), smp(*)
+       real(c_double), intent(inout) :: sion1o(*)
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_bins_snapshot
+     function mistra_bins_redistribute(g, ncell, ff, cm, cw, sap, smp, sion1o, sion1, sl1, nwarn, stream) &
+          result(rc) bind(C, name="mistra_bins_redistribute")
+       import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr, mistra_bins_grid
+       type(mistra_bins_grid), intent(in) :: g
+       integer(c_int64_t), value :: ncell
+       real(c_double), intent(inout) :: ff(*), sion1(*), sl1(*)
+       real(c_double), intent(in) :: cm(*), cw(*), sap(*), smp(*), sion1o(*)
+       integer(c_int32_t), intent(out) :: nwarn(*)
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_bins_redistribute
+  end interface
+end module mistra_bins_mod
+
+module mistra_kon_mod
+  use, intrinsic :: iso_c_binding
+  implicit none
+  type, bind(C) :: mistra_kon_grid
+     integer(c_int32_t) :: nka, nkt
+     real(c_double) :: a0m, dlne
+     type(c_ptr) :: en, rn, b0m, ew, e, dew, rw, qabs   ! rw(nkt,nka), qabs(18,nkt,nka,3)
+  end type mistra_kon_grid
+  interface
+     ! replaces "call subkon(dt, ffk, totr, dfdt, feualt, pp, to, tn, xm1o, xm1n, kr)" (str.f90:4705)
+     ! for ncell layers: ffk(nkt,nka,ncell), totr(18,ncell), the scalars as arrays (ncell)
+     function mistra_kon_subkon(g, ncell, dt, ffk, totr, dfdt, feualt, pp, to, tn, xm1o, xm1n, kr, &
+          status, stream) result(rc) bind(C, name="mistra_kon_subkon")
+       import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr, mistra_kon_grid
+       type(mistra_kon_grid), intent(in) :: g
+       integer(c_int64_t), value :: ncell
+       real(c_double), value :: dt
+       real(c_double), intent(inout) :: ffk(*), to(*), xm1o(*)
+       real(c_double), intent(in) :: totr(*), dfdt(*), feualt(*), pp(*), tn(*), xm1n(*)
+       integer(c_int32_t), intent(in) :: kr(*)
+       integer(c_int32_t), intent(out) :: status(*)
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_kon_subkon
+  end interface
+end module mistra_kon_mod
