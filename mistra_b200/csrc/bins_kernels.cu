@@ -181,7 +181,8 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
   double *s_vcp = s_c0 + NKC * nka;          // [NKC*NKC][nkt] per-jt partial volumes
   double *s_vc = s_vcp + NKC * NKC * nkt;    // [NKC*NKC]
   double *s_den = s_vc + NKC * NKC;          // [NKC]
-  double *s_ds = s_den + NKC;                // [NKC][LSP]
+  double *s_xf = s_den + NKC;                // [NKC*NKC] exchange fraction per (from, to)
+  double *s_ds = s_xf + NKC * NKC;           // [NKC][LSP]
   double *s_c1 = s_ds + NKC * LSP;           // [NKC][nka]  1 - c0
   int *s_kw = (int *)(s_c1 + NKC * nka);     // [nka]
   int *s_ix = s_kw + nka;                    // [NKC][nka]
@@ -189,6 +190,18 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
   const double fpi = 4.0 / 3.0 * 3.1415926535897932;  // str.f90:5838
   const double em6 = (double)1.e-06f;                  // default-REAL literal of str.f90:5983
   for (int i = threadIdx.x; i < nka; i += blockDim.x) { s_en[i] = g.en[i]; s_kw[i] = g.kw[i]; }
+  // bit ia-1 of m_aer: water bin jt = threadIdx.x + 1 of dry class ia is "aerosol" (jt <= kw(ia));
+  // the walk of phase 2 then visits only the classes whose jt belongs to the chem bin
+  unsigned m_aer[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {                    // static indexing keeps the masks in registers
+    unsigned m = 0u;
+    for (int b = 0; b < 32; ++b) {
+      const int ia = 32 * q + b;
+      if (ia < nka && (int)threadIdx.x + 1 <= g.kw[ia]) m |= 1u << b;
+    }
+    m_aer[q] = m;
+  }
 
   for (long long c = blockIdx.x; c < ncell; c += gridDim.x) {
     __syncthreads();
@@ -223,7 +236,7 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
       s_act[threadIdx.x] = act;
       s_den[threadIdx.x] = den;
     }
-    if (threadIdx.x == NKC) s_act[NKC] = 0;  // warn counter
+    if (threadIdx.x == NKC) { s_act[NKC] = 0; s_act[NKC + 1] = 0; }  // warn counter, transfer flag
     for (int i = threadIdx.x; i < NKC * NKC * nkt; i += blockDim.x) s_vcp[i] = 0.0;
     __syncthreads();
     if (any) {
@@ -270,14 +283,36 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
           if (!s_act[kc - 1]) continue;
           int ial, iau;
           ia_range(g, kc, ial, iau);
-          int istart = ial, iend = iau, iinkr = 1;
-          if (s_den[kc - 1] >= 0.0) { istart = iau; iend = ial; iinkr = -1; }
-          for (int ia = istart; iinkr > 0 ? ia <= iend : ia >= iend; ia += iinkr) {
-            const int kwa = s_kw[ia - 1];
-            const bool mine = (kc <= 2) ? (jt <= kwa) : (jt > kwa);
-            if (!mine) continue;
+          const int iinkr = (s_den[kc - 1] >= 0.0) ? -1 : 1;          // str.f90:6016-6020
+          // classes ial..iau whose water bin jt belongs to this chem bin, as bit masks
+          unsigned mk[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int lo = ial - 1 - 32 * q, hi = iau - 32 * q;          // bits [lo, hi) of word q
+            unsigned range = (hi <= 0 || lo >= 32) ? 0u
+                             : ((hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & (lo <= 0 ? 0xffffffffu : ~((1u << lo) - 1u)));
+            mk[q] = range & (kc <= 2 ? m_aer[q] : ~m_aer[q]);
+          }
+          for (;;) {
+            int ia;                                                       // next class in walk order
+            if (iinkr > 0) {
+              if (mk[0]) { const int b = __ffs(mk[0]) - 1; mk[0] &= mk[0] - 1; ia = b + 1; }
+              else if (mk[1]) { const int b = __ffs(mk[1]) - 1; mk[1] &= mk[1] - 1; ia = b + 33; }
+              else if (mk[2]) { const int b = __ffs(mk[2]) - 1; mk[2] &= mk[2] - 1; ia = b + 65; }
+              else if (mk[3]) { const int b = __ffs(mk[3]) - 1; mk[3] &= mk[3] - 1; ia = b + 97; }
+              else break;
+            } else {
+              if (mk[3]) { const int b = 31 - __clz(mk[3]); mk[3] ^= 1u << b; ia = b + 97; }
+              else if (mk[2]) { const int b = 31 - __clz(mk[2]); mk[2] ^= 1u << b; ia = b + 65; }
+              else if (mk[1]) { const int b = 31 - __clz(mk[1]); mk[1] ^= 1u << b; ia = b + 33; }
+              else if (mk[0]) { const int b = 31 - __clz(mk[0]); mk[0] ^= 1u << b; ia = b + 1; }
+              else break;
+            }
             const double x1 = t_ff[(ia - 1) * nkt + jt - 1];
-            if (x1 > 0.0) {
+            // x1 > 0 on the integer pipe (an FP64 compare costs ~45 cycles here and most bins are
+            // empty): positive doubles are exactly the positive int64 patterns, NaNs excluded
+            const long long xb = __double_as_longlong(x1);
+            if (xb > 0 && xb <= 0x7ff0000000000000LL) {
               const int ix = s_ix[(kc - 1) * nka + ia - 1];
               const double c0 = s_c0[(kc - 1) * nka + ia - 1];
               const double a = __dmul_rn(x1, c0), b = __dmul_rn(x1, s_c1[(kc - 1) * nka + ia - 1]);
@@ -316,30 +351,42 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
       tile_store(f, t_ff, ntile);
       __syncthreads();
       // ---- phase 4: exchange of dissolved species between bins (str.f90:6102-6134) ----
-      for (int pass = 0; pass < 2; ++pass) {
-        const int nl = pass == 0 ? J2 : J6;
-        double *base = (pass == 0 ? sl1 : sion1) + (size_t)c * NKC * nl;
-        for (int l = threadIdx.x; l < nl; l += blockDim.x) {
+      // exchange fraction of every (from, to) pair once (0 = no transfer) ...
+      if (threadIdx.x < NKC * NKC) {
+        const int kc = threadIdx.x / NKC, kkc = threadIdx.x % NKC;
+        double xfact = 0.0;
+        const double vcv = s_vc[threadIdx.x];
+        if (kc != kkc && kc < g.nkc_l && kkc < g.nkc_l && vcv != 0.0) {
+          const double cwf = cw[c * NKC + kc];
+          if (cwf > 0.0) {
+            const double vol_ch = __dmul_rn(vcv, 1.e-12);
+            xfact = __dadd_rn(1.0, -__ddiv_rn(__dadd_rn(cwf, -vol_ch), cwf));
+            s_act[NKC + 1] = 1;                       // at least one transfer in this layer
+          }
+        }
+        s_xf[threadIdx.x] = xfact;
+      }
+      __syncthreads();
+      // ... then every species l of sl1 (121) and sion1 (55) walks the pairs in the reference's order
+      if (s_act[NKC + 1]) {
+        for (int l = threadIdx.x; l < J2 + J6; l += blockDim.x) {
+          const int nl = l < J2 ? J2 : J6, ll = l < J2 ? l : l - J2;
+          double *base = (l < J2 ? sl1 : sion1) + (size_t)c * NKC * nl;
           double v[NKC];
-          for (int k = 0; k < NKC; ++k) v[k] = base[k * nl + l];
-          bool touched = false;
-          for (int kc = 0; kc < g.nkc_l; ++kc)
-            for (int kkc = 0; kkc < g.nkc_l; ++kkc) {
-              if (kkc == kc) continue;
-              const double vcv = s_vc[kc * NKC + kkc];
-              if (vcv == 0.0) continue;
-              const double cwf = cw[c * NKC + kc];
-              if (cwf > 0.0) {
-                const double vol_ch = __dmul_rn(vcv, 1.e-12);
-                const double xfact = __dadd_rn(1.0, -__ddiv_rn(__dadd_rn(cwf, -vol_ch), cwf));
-                const double xch = __dmul_rn(v[kc], xfact);
-                v[kc] = __dadd_rn(v[kc], -xch);
-                v[kkc] = __dadd_rn(v[kkc], xch);
-                touched = true;
-              }
+#pragma unroll
+          for (int k = 0; k < NKC; ++k) v[k] = base[k * nl + ll];
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc)
+#pragma unroll
+            for (int kkc = 0; kkc < NKC; ++kkc) {            // pairs outside nkc_l have xfact = 0
+              const double xfact = s_xf[kc * NKC + kkc];
+              if (kkc == kc || xfact == 0.0) continue;     // xfact == 0 moves nothing (xch = 0)
+              const double xch = __dmul_rn(v[kc], xfact);
+              v[kc] = __dadd_rn(v[kc], -xch);
+              v[kkc] = __dadd_rn(v[kkc], xch);
             }
-          if (touched)
-            for (int k = 0; k < NKC; ++k) base[k * nl + l] = v[k];
+#pragma unroll
+          for (int k = 0; k < NKC; ++k) base[k * nl + ll] = v[k];
         }
       }
     }
@@ -459,7 +506,7 @@ size_t smem_snapshot(const mistra_bins_grid *g)
 size_t smem_redistribute(const mistra_bins_grid *g)
 {
   const size_t nka = g->nka, nkt = g->nkt;
-  return sizeof(double) * (nka * nkt + nka + 2 * NKC * nka + NKC * NKC * nkt + NKC * NKC + NKC + NKC * LSP) +
+  return sizeof(double) * (nka * nkt + nka + 2 * NKC * nka + NKC * NKC * nkt + 2 * NKC * NKC + NKC + NKC * LSP) +
          sizeof(int) * (nka + NKC * nka + NKC + 4);
 }
 

@@ -80,10 +80,15 @@ def greedy_order(uses):
 
 
 class Emitter:
-    def __init__(self, m, unroll_decomp, tail=0, solve_tail=0):
+    def __init__(self, m, unroll_decomp, tail=0):
         self.m = m
         self.tail = tail
-        self.solve_tail = solve_tail
+        # structural fill-in of the LU pattern: Jac_SP sets these to 0 (gas.f:2675-6100), so after
+        # Ghimj = -Jac0 they are -0.0 - no need to store and re-load them
+        diag = set(int(d) for d in m.diag[:m.nvar])
+        self.fill = set(nz for nz in range(m.lu_nonzero) if not m.jvs[nz] and nz not in diag)
+        touched = set(op[2] for op in m.decomp_ops() if op[0] == "upd")
+        assert self.fill <= touched, "a fill-in entry that no elimination step writes"
         self.x = m.suffix
         self.unroll_decomp = unroll_decomp
         self.coef = {c: i for i, c in enumerate(c for c in m.coef_literals if not c.isdigit())}
@@ -234,7 +239,9 @@ class Emitter:
                     w("  { const double g = -(%s) + ghinv; G_(%d) = g; sing |= (g == 0.0); }" % (e, nz))
             else:
                 if e is None:
-                    w("  G_(%d) = -0.0;" % nz)
+                    assert nz in self.fill
+                    if self.unroll_decomp != "tiled":   # the tiled LU creates fill-in in registers (gload)
+                        w("  G_(%d) = -0.0;" % nz)
                 else:
                     w("  G_(%d) = -(%s);" % (nz, e))
         w("#undef V_")
@@ -298,6 +305,10 @@ class Emitter:
         w("}")
         w("")
 
+    def gload(self, idx):
+        """First read of an LU slot by the factorisation: fill-in starts as -0.0."""
+        return "-0.0" if idx in self.fill else "G_(%d)" % idx
+
     # -- tile-blocked LU ---------------------------------------------------------
     def _emit_row_program(self, k, head_only_below=None):
         """Row-wise elimination of row k (KppDecomp order).  With head_only_below = h
@@ -336,7 +347,7 @@ class Emitter:
         def need(r):
             if r not in loaded:
                 loaded.add(r)
-                w("    double r%d = G_(%d);" % (r, r))
+                w("    double r%d = %s;" % (r, self.gload(r)))
 
         for n, op in enumerate(prog):
             if op[0] == "piv":
@@ -402,7 +413,7 @@ class Emitter:
                 reg = {e: "c%d" % idx for e, idx in ent.items()}
                 w("  {  // tile (%d,%d): %d entries" % (I, J, len(ent)))
                 for e, idx in sorted(ent.items(), key=lambda t: t[1]):
-                    w("    double %s = G_(%d);" % (reg[e], idx))
+                    w("    double %s = %s;" % (reg[e], self.gload(idx)))
                 # candidate pivots
                 ks = set()
                 for i in R:
@@ -501,94 +512,32 @@ class Emitter:
         w("{")
         w("#define X_(i) EL(MODE == 1 ? S_K1 : (MODE == 2 ? S_K2 : S_K3), i)")
         w("  double esum = 0.0;")
-        tiled = self.unroll_decomp == "tiled" and self.solve_tail > 0
+
+        def XR(i):
+            return "X_(%d)" % int(i)
 
         def fwd_row(k):
             lo, dg = int(m.crow[k]), int(m.diag[k])
             if dg > lo:
-                s = "  X_(%d) = X_(%d)" % (k, k)
+                s = "  %s = %s" % (XR(k), XR(k))
                 for kk in range(lo, dg):
-                    s += " - G_(%d) * X_(%d)" % (kk, m.icol[kk])
+                    s += " - G_(%d) * %s" % (kk, XR(m.icol[kk]))
                 w(s + ";")
 
         def bwd_row(k):
             dg, hi = int(m.diag[k]), int(m.crow[k + 1])
-            s = "X_(%d)" % k
+            s = XR(k)
             for kk in range(dg + 1, hi):
-                s += " - G_(%d) * X_(%d)" % (kk, m.icol[kk])
+                s += " - G_(%d) * %s" % (kk, XR(m.icol[kk]))
             w("  {")
             w("    const double x = PIV_APPLY(%s, G_(%d));" % (s, dg))
             w("    SOLVE_EPILOGUE(%d)" % k)
             w("  }")
 
-        if tiled:
-            w("#ifdef KPP_STRICT   // reference statement order (KppSolve, gas.f:6206-6636)")
         for k in range(m.nvar):
             fwd_row(k)
         for k in range(m.nvar - 1, -1, -1):
             bwd_row(k)
-        if tiled:
-            # Row blocks of B over the trailing region: the B right-hand-side entries of a
-            # block stay in registers while each loaded X(k) serves every row of the block
-            # (B independent FP64 chains per lane).  Forward sweep: same order as the
-            # reference per row.  Backward sweep: the columns right of the block are applied
-            # before the block's own columns - a reassociation of the row's dot product
-            # (product build only; the strict build above keeps the reference order).
-            B = 8
-            n = m.nvar
-            tail = min(self.solve_tail, n) // B * B
-            h = n - tail
-            pos = m.pos
-            w("#else               // row-blocked sweeps over the trailing %d rows" % tail)
-            for k in range(h):
-                fwd_row(k)
-            for I in range(tail // B):
-                R = list(range(h + I * B, h + I * B + B))
-                w("  {")
-                for i in R:
-                    w("    double x%d = X_(%d);" % (i, i))
-                ks = sorted(set(int(m.icol[kk]) for i in R for kk in range(int(m.crow[i]), int(m.diag[i]))))
-                for k in ks:
-                    rows = [i for i in R if i > k and (i, k) in pos]
-                    if not rows:
-                        continue
-                    if k < R[0]:
-                        w("    { const double xk = X_(%d);" % k)
-                        for i in rows:
-                            w("      x%d -= G_(%d) * xk;" % (i, pos[(i, k)]))
-                        w("    }")
-                    else:
-                        for i in rows:
-                            w("    x%d -= G_(%d) * x%d;" % (i, pos[(i, k)], k))
-                for i in R:
-                    w("    X_(%d) = x%d;" % (i, i))
-                w("  }")
-            for I in range(tail // B - 1, -1, -1):
-                R = list(range(h + I * B, h + I * B + B))
-                w("  {")
-                for i in R:
-                    w("    double a%d = X_(%d);" % (i, i))
-                cs = sorted(set(int(m.icol[kk]) for i in R for kk in range(int(m.diag[i]) + 1, int(m.crow[i + 1]))))
-                for c in cs:
-                    if c <= R[-1]:
-                        continue
-                    rows = [i for i in R if (i, c) in pos]
-                    w("    { const double xc = X_(%d);" % c)
-                    for i in rows:
-                        w("      a%d -= G_(%d) * xc;" % (i, pos[(i, c)]))
-                    w("    }")
-                for i in reversed(R):
-                    for c in R:
-                        if c > i and (i, c) in pos:
-                            w("    a%d -= G_(%d) * f%d;" % (i, pos[(i, c)], c))
-                    w("    double f%d;" % i)
-                    w("    { const double x = PIV_APPLY(a%d, G_(%d)); f%d = x;" % (i, int(m.diag[i]), i))
-                    w("      SOLVE_EPILOGUE(%d)" % i)
-                    w("    }")
-                w("  }")
-            for k in range(h - 1, -1, -1):
-                bwd_row(k)
-            w("#endif")
         w("#undef X_")
         w("  return esum;")
         w("}")
@@ -622,9 +571,6 @@ def main(argv):
     # of the given size (covers >= 96 % of the multiply-adds)
     unroll = {"gas": "tiled", "aer": "tiled", "tot": "tiled"}
     tail = {"gas": 32, "aer": 96, "tot": 128}
-    # rows of the row-blocked triangular sweeps; 0 = row-wise.  Measured on B200 (round 1): no gain
-    # (the X re-reads it removes were L1/L2 hits), so it stays off.
-    solve_tail = {"gas": 0, "aer": 0, "tot": 0}
     for a in argv[1:]:
         if a.startswith("--lu="):           # e.g. --lu=gas:rows,aer:loop
             for kv in a.split("=", 1)[1].split(","):
@@ -636,7 +582,7 @@ def main(argv):
                 tail[n] = int(v)
     for name in mechmod.MECH_NAMES:
         m = mechmod.load(name)
-        text = Emitter(m, unroll[name], tail[name], solve_tail[name]).emit()
+        text = Emitter(m, unroll[name], tail[name]).emit()
         path = os.path.join(outdir, "mech_%s.cuh" % m.suffix)
         if not (os.path.exists(path) and open(path).read() == text):
             with open(path, "w") as f:
