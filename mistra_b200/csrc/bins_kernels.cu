@@ -178,8 +178,8 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
   double *t_ff = sm;                         // [nka][nkt]
   double *s_en = t_ff + ntile;               // [nka]
   double *s_c0 = s_en + nka;                 // [NKC][nka]
-  double *s_vcp = s_c0 + NKC * nka;          // [NKC*NKC][nkt] per-jt partial volumes
-  double *s_vc = s_vcp + NKC * NKC * nkt;    // [NKC*NKC]
+  double *s_vcw = s_c0 + NKC * nka;          // [warps][NKC*NKC] per-warp partial volumes
+  double *s_vc = s_vcw + (BINS_THREADS / 32) * NKC * NKC;   // [NKC*NKC]
   double *s_den = s_vc + NKC * NKC;          // [NKC]
   double *s_xf = s_den + NKC;                // [NKC*NKC] exchange fraction per (from, to)
   double *s_ds = s_xf + NKC * NKC;           // [NKC][LSP]
@@ -237,7 +237,7 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
       s_den[threadIdx.x] = den;
     }
     if (threadIdx.x == NKC) { s_act[NKC] = 0; s_act[NKC + 1] = 0; }  // warn counter, transfer flag
-    for (int i = threadIdx.x; i < NKC * NKC * nkt; i += blockDim.x) s_vcp[i] = 0.0;
+    for (int i = threadIdx.x; i < (BINS_THREADS / 32) * NKC * NKC; i += blockDim.x) s_vcw[i] = 0.0;
     __syncthreads();
     if (any) {
       // ---- phase 1: target class ix and split c0 of every (kc, ia) (str.f90:6023-6044) ----
@@ -278,9 +278,10 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
       __syncthreads();
       // ---- phase 2: one thread per water bin jt walks the dry classes (str.f90:6012-6096) ----
       const int jt = threadIdx.x + 1;
-      if (jt <= nkt) {
+      {
         for (int kc = 1; kc <= g.nkc_l; ++kc) {
           if (!s_act[kc - 1]) continue;
+          double vq1 = 0.0, vq2 = 0.0, vq3 = 0.0, vq4 = 0.0;   // volume moved to chem bins 1..4 by this jt
           int ial, iau;
           ia_range(g, kc, ial, iau);
           const int iinkr = (s_den[kc - 1] >= 0.0) ? -1 : 1;          // str.f90:6016-6020
@@ -291,7 +292,7 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
             const int lo = ial - 1 - 32 * q, hi = iau - 32 * q;          // bits [lo, hi) of word q
             unsigned range = (hi <= 0 || lo >= 32) ? 0u
                              : ((hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & (lo <= 0 ? 0xffffffffu : ~((1u << lo) - 1u)));
-            mk[q] = range & (kc <= 2 ? m_aer[q] : ~m_aer[q]);
+            mk[q] = (jt <= nkt) ? (range & (kc <= 2 ? m_aer[q] : ~m_aer[q])) : 0u;
           }
           for (;;) {
             int ia;                                                       // next class in walk order
@@ -330,22 +331,36 @@ bins_redistribute_kernel(GridDev g, long long ncell, double *__restrict__ ff,
                 r3 = __dmul_rn(__dmul_rn(r, r), r);
               }
               if (tix != kc) {
-                double *v = &s_vcp[((kc - 1) * NKC + tix - 1) * nkt + jt - 1];
-                *v = __dadd_rn(*v, __dmul_rn(__dmul_rn(a, fpi), r3));
+                const double dv = __dmul_rn(__dmul_rn(a, fpi), r3);
+                if (tix == 1) vq1 = __dadd_rn(vq1, dv); else if (tix == 2) vq2 = __dadd_rn(vq2, dv);
+                else if (tix == 3) vq3 = __dadd_rn(vq3, dv); else vq4 = __dadd_rn(vq4, dv);
               }
               if (tixp != kc) {
-                double *v = &s_vcp[((kc - 1) * NKC + tixp - 1) * nkt + jt - 1];
-                *v = __dadd_rn(*v, __dmul_rn(__dmul_rn(b, fpi), r3));
+                const double dv = __dmul_rn(__dmul_rn(b, fpi), r3);
+                if (tixp == 1) vq1 = __dadd_rn(vq1, dv); else if (tixp == 2) vq2 = __dadd_rn(vq2, dv);
+                else if (tixp == 3) vq3 = __dadd_rn(vq3, dv); else vq4 = __dadd_rn(vq4, dv);
               }
             }
+          }
+          // fixed-tree reduction over the warp's water bins (deterministic), one partial per warp
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            vq1 = __dadd_rn(vq1, __shfl_xor_sync(0xffffffffu, vq1, off));
+            vq2 = __dadd_rn(vq2, __shfl_xor_sync(0xffffffffu, vq2, off));
+            vq3 = __dadd_rn(vq3, __shfl_xor_sync(0xffffffffu, vq3, off));
+            vq4 = __dadd_rn(vq4, __shfl_xor_sync(0xffffffffu, vq4, off));
+          }
+          if ((threadIdx.x & 31) == 0) {
+            double *o = s_vcw + (threadIdx.x >> 5) * NKC * NKC + (kc - 1) * NKC;
+            o[0] = vq1; o[1] = vq2; o[2] = vq3; o[3] = vq4;
           }
         }
       }
       __syncthreads();
-      // ---- phase 3: transferred volume per (from, to) pair, summed in jt order ----
+      // ---- phase 3: transferred volume per (from, to) pair: the warps' partials in warp order ----
       if (threadIdx.x < NKC * NKC) {
         double s = 0.0;
-        for (int j = 0; j < nkt; ++j) s = __dadd_rn(s, s_vcp[threadIdx.x * nkt + j]);
+        for (int wq = 0; wq < BINS_THREADS / 32; ++wq) s = __dadd_rn(s, s_vcw[wq * NKC * NKC + threadIdx.x]);
         s_vc[threadIdx.x] = s;
       }
       tile_store(f, t_ff, ntile);
@@ -506,7 +521,7 @@ size_t smem_snapshot(const mistra_bins_grid *g)
 size_t smem_redistribute(const mistra_bins_grid *g)
 {
   const size_t nka = g->nka, nkt = g->nkt;
-  return sizeof(double) * (nka * nkt + nka + 2 * NKC * nka + NKC * NKC * nkt + 2 * NKC * NKC + NKC + NKC * LSP) +
+  return sizeof(double) * (nka * nkt + nka + 2 * NKC * nka + (BINS_THREADS / 32 + 2) * NKC * NKC + NKC + NKC * LSP) +
          sizeof(int) * (nka + NKC * nka + NKC + 4);
 }
 
