@@ -101,8 +101,26 @@ module mistra_kon_mod
      integer(c_int32_t) :: nka, nkt
      real(c_double) :: a0m, dlne
      type(c_ptr) :: en, rn, b0m, ew, e, dew, rw, qabs   ! rw(nkt,nka), qabs(18,nkt,nka,3)
+     type(c_ptr) :: kw, rq                              ! kw(nka) int32, rq(nkt,nka)  (mistra_kon_layers)
+     integer(c_int32_t) :: ka, reserved
   end type mistra_kon_grid
+  ! mistra_kon_state: c_loc pointers to the COMMON arrays of kon, first layer of the batch
+  type, bind(C) :: mistra_kon_state
+     type(c_ptr) :: ff, t, talt, xm1, xm1a, feu, dfddt, xm2, dtcon, p, totrad, nar
+     type(c_ptr) :: vol1_a, vol1_d, part_o_a, part_o_d, part_n_a, part_n_d, vol2, pntot, status
+  end type mistra_kon_state
   interface
+     ! replaces the layer loop of SUBROUTINE kon (str.f90:4615-4772)
+     function mistra_kon_layers(g, ncell, dt, chem, st, stream) result(rc) bind(C, name="mistra_kon_layers")
+       import :: c_int, c_int64_t, c_double, c_ptr, mistra_kon_grid, mistra_kon_state
+       type(mistra_kon_grid), intent(in) :: g
+       integer(c_int64_t), value :: ncell
+       real(c_double), value :: dt
+       integer(c_int), value :: chem
+       type(mistra_kon_state), intent(in) :: st
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_kon_layers
      ! replaces "call subkon(dt, ffk, totr, dfdt, feualt, pp, to, tn, xm1o, xm1n, kr)" (str.f90:4705)
      ! for ncell layers: ffk(nkt,nka,ncell), totr(18,ncell), the scalars as arrays (ncell)
      function mistra_kon_subkon(g, ncell, dt, ffk, totr, dfdt, feualt, pp, to, tn, xm1o, xm1n, kr, &

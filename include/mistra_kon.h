@@ -54,6 +54,11 @@ typedef struct mistra_kon_grid {
   const double *dew;     /* [nkt]  bin width [mg]                                     */
   const double *rw;      /* [nka][nkt] = rw(nkt,nka) radius at the upper bin limit [um] */
   const double *qabs;    /* [3][nka][nkt][18] = qabs(18,nkt,nka,jptaerrad)            */
+  /* only read by mistra_kon_layers (may be NULL / 0 for mistra_kon_subkon): */
+  const int32_t *kw;     /* [nka]  COMMON /blck06/ kw (1-based limit aerosol|droplet)   */
+  const double *rq;      /* [nka][nkt] = rq(nkt,nka) radius at the bin mean [um]        */
+  int32_t ka;            /* COMMON /blck06/ ka                                          */
+  int32_t reserved;
 } mistra_kon_grid;
 
 /* HOST buffers (staged to the current device and back; synchronous). */
@@ -68,6 +73,37 @@ int mistra_kon_subkon_device(const mistra_kon_grid *g, int64_t ncell, double dt,
                              const double *d_pp, double *d_to, const double *d_tn,
                              double *d_xm1o, const double *d_xm1n, const int32_t *d_kr,
                              int32_t *d_status, void *stream);
+
+/* The whole layer loop of SUBROUTINE kon (str.f90:4615-4772) for ncell layers at once:
+ * per layer, with chem, the bin sums before the step (vol1_a/d, part_o_a/d, vol2;
+ * 4625-4659); then either the dry branch feu(k) < 0.7 - feu from xm1 and SUBROUTINE equil
+ * case 1 (Koehler equilibrium size of every dry class by FUNCTION rgl, str.f90:4801-4981,
+ * 2164-2251), which also updates xm2 - or the humid branch: subkon as above followed by the
+ * write-back t = talt = to, xm1 = xm1a = xm1o, feu, dfddt, xm2, dtcon (4708-4721); then, with
+ * chem, the sums after the step (part_n_a/d, pntot; 4724-4770).  What stays on the host:
+ * the cloud base/top search (4775-4782, a scan over k) and konc.
+ * Arrays are the reference's COMMON arrays with the layer index last; all [ncell] unless
+ * noted.  With chem == 0 the eight sum arrays may be NULL.
+ * status: 0 = dry branch taken, 1..10 / -1 / -2 as for mistra_kon_subkon. */
+typedef struct mistra_kon_state {
+  double *ff;                      /* [ncell][nka][nkt] COMMON /cb52/  in/out            */
+  double *t, *talt;                /* COMMON /cb53/   in/out                              */
+  double *xm1, *xm1a, *feu, *dfddt;/* COMMON /cb54/   in/out                              */
+  double *xm2;                     /* COMMON /cb54/   out                                 */
+  double *dtcon;                   /* COMMON /cb48/   out                                 */
+  const double *p;                 /* COMMON /cb53/                                       */
+  const double *totrad;            /* [ncell][18] COMMON /cb11/                           */
+  const int32_t *nar;              /* COMMON /cb52/                                       */
+  double *vol1_a, *vol1_d, *part_o_a, *part_o_d, *part_n_a, *part_n_d; /* [ncell][nka]   */
+  double *vol2, *pntot;            /* [ncell][4]  COMMON /blck07/, /blck08/               */
+  int32_t *status;                 /* or NULL                                             */
+} mistra_kon_state;
+
+/* HOST buffers (synchronous) / DEVICE buffers (asynchronous on `stream`). */
+int mistra_kon_layers(const mistra_kon_grid *g, int64_t ncell, double dt, int chem,
+                      const mistra_kon_state *s, void *stream);
+int mistra_kon_layers_device(const mistra_kon_grid *g, int64_t ncell, double dt, int chem,
+                             const mistra_kon_state *d_s, void *stream);
 
 int64_t mistra_kon_launch_count(void);
 

@@ -33,10 +33,50 @@ constexpr int KON_THREADS = 128;
 constexpr int MAXK = 128;
 
 struct KonGridDev {
-  int nka, nkt;
+  int nka, nkt, ka;
   double a0m, dlne;
-  const double *en, *rn, *b0m, *ew, *e, *dew, *rw, *qabs;
+  const double *en, *rn, *b0m, *ew, *e, *dew, *rw, *qabs, *rq;
+  const int *kw;
 };
+
+// Per-layer arrays.  Two views of the same kernel:
+//  * subkon view (full == 0): the arguments of "call subkon" (str.f90:4705);
+//  * kon view (full == 1): the COMMON arrays the layer loop of SUBROUTINE kon reads and
+//    writes (str.f90:4615-4772), incl. the dry branch (equil) and, with chem, the bin sums.
+struct KonArgs {
+  int full, chem;
+  double *ff;                                   // [ncell][nka][nkt] in/out
+  const double *totr;                           // [ncell][18]
+  const double *pp;                             // [ncell]
+  const int *kr;                                // [ncell] nar(k)
+  int *status;                                  // [ncell] or null
+  // subkon view
+  const double *dfdt, *feualt, *tn, *xm1n;      // in
+  double *to, *xm1o;                            // in/out
+  // kon view
+  double *t, *talt, *xm1, *xm1a, *feu, *dfddt, *xm2, *dtcon;
+  double *vol1_a, *vol1_d, *part_o_a, *part_o_d, *part_n_a, *part_n_d;   // [ncell][nka] or null
+  double *vol2, *pntot;                                                  // [ncell][4]   or null
+};
+
+// FUNCTION rgl (str.f90:2164-2251): equilibrium radius of a solution droplet at relative
+// humidity feu < 1 by Newton iteration on the Koehler equation.
+__device__ double rgl(double r_dry, double a, double b, double feu)
+{
+  if (feu >= 1.0) return r_dry;
+  const double zlogf = log(feu);
+  const double alpha = a / r_dry;
+  double xalt = exp(feu), xneu = xalt;
+  for (int ij = 1; ij <= 100; ++ij) {
+    const double x3 = xalt * xalt * xalt;
+    const double falt = (x3 - 1.0) * (xalt * zlogf - alpha) + b * xalt;
+    const double fstralt = (4.0 * x3 - 1.0) * zlogf - 3.0 * (xalt * xalt) * alpha + b;
+    xneu = xalt - falt / fstralt;
+    if (fabs(xneu - xalt) < 1.e-7 * xalt) break;
+    xalt = xneu;
+  }
+  return r_dry * xneu;
+}
 
 // constants.f90:48-83
 __device__ constexpr double kGasConst = 8.3144743, kMair = 28.96546e-3, kMwat = 18.01528e-3;
@@ -159,13 +199,11 @@ __device__ int advec_row(int nkt, double dt, const RowCoef &rc, const double *__
 }
 
 __global__ void __launch_bounds__(KON_THREADS)
-kon_subkon_kernel(KonGridDev g, long long ncell, double dt, double *__restrict__ ffk_all,
-                  const double *__restrict__ totr_all, const double *__restrict__ dfdt_a,
-                  const double *__restrict__ feualt_a, const double *__restrict__ pp_a,
-                  double *__restrict__ to_a, const double *__restrict__ tn_a,
-                  double *__restrict__ xm1o_a, const double *__restrict__ xm1n_a,
-                  const int *__restrict__ kr_a, int *__restrict__ status)
+kon_subkon_kernel(KonGridDev g, long long ncell, double dt, KonArgs A)
 {
+  double *__restrict__ ffk_all = A.ff;
+  const double *__restrict__ totr_all = A.totr;
+  int *__restrict__ status = A.status;
   extern __shared__ __align__(16) double sm[];
   const int nka = g.nka, nkt = g.nkt, ntile = nka * nkt;
   double *s_cd = sm, *s_cr = s_cd + ntile, *s_sr = s_cr + ntile, *s_falt = s_sr + ntile, *s_ffk = s_falt + ntile;
@@ -193,8 +231,67 @@ kon_subkon_kernel(KonGridDev g, long long ncell, double dt, double *__restrict__
       for (int i = threadIdx.x; i < ntile; i += blockDim.x) cp_async8(s_falt + i, ffk + i);
     if (threadIdx.x < MB) s_totr[threadIdx.x] = totr_all[c * MB + threadIdx.x];
     // ---- layer scalars (str.f90:5104-5127), by every thread ----
-    const double to0 = to_a[c], xm1o0 = xm1o_a[c], tn = tn_a[c], xm1n = xm1n_a[c], pp = pp_a[c];
-    const double feualt = feualt_a[c];
+    // subkon's arguments; in the kon view they come from the COMMON arrays (str.f90:4676-4703)
+    const double to0 = A.full ? A.talt[c] : A.to[c], xm1o0 = A.full ? A.xm1a[c] : A.xm1o[c];
+    const double tn = A.full ? A.t[c] : A.tn[c], xm1n = A.full ? A.xm1[c] : A.xm1n[c], pp = A.pp[c];
+    const double feualt = A.full ? A.feu[c] : A.feualt[c];
+    const double dfdt_c = A.full ? A.dfddt[c] : A.dfdt[c];
+    const bool dry = A.full && feualt < 0.7;          // str.f90:4663: Koehler equilibrium instead
+    if (A.full) {
+      // the tile is needed right away (bin sums, dry branch)
+      cp_async_wait_all();
+      __syncthreads();
+      if (A.chem) {
+        // particle number and volume per dry class before the step (str.f90:4625-4659)
+        if (threadIdx.x < nka) {
+          const int ia = threadIdx.x, kwa = g.kw[ia];
+          const double z4pi3 = 4.0 * kPi / 3.0;
+          double va = 0.0, pa = 0.0, vd = 0.0, pd = 0.0;
+          for (int jt = 0; jt < nkt; ++jt) {
+            const double f = s_falt[ia * nkt + jt], r = g.rq[ia * nkt + jt];
+            const double v = f * z4pi3 * (r * r * r);
+            if (jt < kwa) { va = va + v; pa = pa + f; } else { vd = vd + v; pd = pd + f; }
+          }
+          A.vol1_a[c * nka + ia] = va; A.part_o_a[c * nka + ia] = pa;
+          A.vol1_d[c * nka + ia] = vd; A.part_o_d[c * nka + ia] = pd;
+          s_cd[ia] = va; s_cd[nka + ia] = vd;        // scratch: the coefficient tile is not set up yet
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {                       // vol2(1..4): sums over the classes of the bin
+          const int kc = threadIdx.x, lo = (kc & 1) ? g.ka : 0, hi = (kc & 1) ? nka : g.ka;
+          double sacc = 0.0;
+          for (int ia = lo; ia < hi; ++ia) sacc = sacc + s_cd[(kc >= 2 ? nka : 0) + ia];
+          A.vol2[c * 4 + kc] = sacc;
+        }
+        __syncthreads();
+      }
+    }
+    if (dry) {
+      // ---- SUBROUTINE equil, case 1 (str.f90:4801-4981) on this layer ----
+      const double feun = xm1n * pp / ((0.62198 + 0.37802 * xm1n) * p21(tn));   // str.f90:4664
+      const double a0e = g.a0m / tn;
+      if (threadIdx.x < nka) {
+        const int ia = threadIdx.x;
+        double tot = 0.0;
+        for (int jt = 0; jt < nkt; ++jt) { tot = tot + s_falt[ia * nkt + jt]; s_ffk[ia * nkt + jt] = 0.0; }
+        const double rn = g.rn[ia];
+        const double rg = rgl(rn, a0e, g.b0m[ia] * 2.0, feun);       // zrho_frac = rho3/rhow = 2
+        const double eg = (4.e-09 * kPi / 3.0) * (rg * rg * rg - rn * rn * rn);
+        int jt = 1;
+        while (jt < nkt && eg > g.ew[jt - 1]) jt = jt + 1;          // (clamped at the last bin)
+        s_ffk[ia * nkt + jt - 1] = tot;
+        s_dw[ia] = tot * s_e[jt - 1];                               // this class' share of xm2
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double x2 = 0.0;
+        for (int ia = 0; ia < nka; ++ia) x2 = x2 + s_dw[ia];
+        A.feu[c] = feun;
+        A.xm2[c] = x2;
+        A.dtcon[c] = 0.0;
+        if (status) status[c] = 0;
+      }
+    } else {
     const double zxl21 = xl21(to0);
     const double xldcp = zxl21 / kCp;
     const double xka = therm_conduct_air(to0);
@@ -207,7 +304,7 @@ kon_subkon_kernel(KonGridDev g, long long ncell, double dt, double *__restrict__
     const double a0 = g.a0m / to0;
     const double xdv0 = xdv * sqrt(2.0 * kPi / (r1 * to0)) / 3.6e-08;
     const double xka0 = xka * sqrt(2.0 * kPi / (r0 * to0)) / (7.e-07 * rho * kCp);
-    const int kr = kr_a[c];
+    const int kr = A.kr[c];
     __syncthreads();  // s_totr visible
     const int ib0 = (s_totr[0] < 1.0) ? 7 : 1;
     // ---- growth-rate coefficients over the grid (str.f90:5128-5149) ----
@@ -230,7 +327,7 @@ kon_subkon_kernel(KonGridDev g, long long ncell, double dt, double *__restrict__
       s_cr[q] = rad * 7.5e5 / (rk * x1) - kRhow * 4190. * (tn - to0) / (dt * x1);
     }
     // ---- secant iteration on the mean saturation ratio (str.f90:5151-5201) ----
-    double feuneu = feualt + dfdt_a[c] * dt;
+    double feuneu = feualt + dfdt_c * dt;
     if (feualt < 0.95) feuneu = xm1n * pp / (p21(tn) * (.62198 + .37802 * xm1n));
     double fquer = 0.5 * (feuneu + feualt);
     double res = 0.0, fqa = 0.0, to = to0, xm1o = xm1o0;
@@ -280,18 +377,58 @@ kon_subkon_kernel(KonGridDev g, long long ncell, double dt, double *__restrict__
       fquer = s_it[0];
       if (s_flag[0]) break;
     }
-    // ---- write back ----
+    // ---- write back of the humid branch (str.f90:4708-4721) ----
+    if (threadIdx.x < nka && A.full) {               // xm2: liquid water, per class then over classes
+      double x2 = 0.0;
+      for (int jt = 0; jt < nkt; ++jt) x2 = x2 + s_ffk[threadIdx.x * nkt + jt] * s_e[jt];
+      s_dw[threadIdx.x] = x2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (A.full) {
+        A.t[c] = to; A.talt[c] = to; A.xm1[c] = xm1o; A.xm1a[c] = xm1o;
+        const double fn = xm1o * pp / ((0.62198 + 0.37802 * xm1o) * p21(to));
+        A.feu[c] = fn;
+        A.dfddt[c] = (fn - feualt) / dt;
+        double x2 = 0.0;
+        for (int ia = 0; ia < nka; ++ia) x2 = x2 + s_dw[ia];
+        A.xm2[c] = x2;
+        A.dtcon[c] = (to - tn) / dt;
+      } else {
+        A.to[c] = to;
+        A.xm1o[c] = xm1o;
+      }
+      if (status) status[c] = st;
+    }
+    }  // humid branch
+    __syncthreads();
+    if (A.full && A.chem) {
+      // particle number per class and bin after the step (str.f90:4724-4770)
+      if (threadIdx.x < nka) {
+        const int ia = threadIdx.x, kwa = g.kw[ia];
+        double pa = 0.0, pd = 0.0;
+        for (int jt = 0; jt < nkt; ++jt) {
+          const double f = s_ffk[ia * nkt + jt];
+          if (jt < kwa) pa = pa + f; else pd = pd + f;
+        }
+        A.part_n_a[c * nka + ia] = pa; A.part_n_d[c * nka + ia] = pd;
+        s_cd[ia] = pa; s_cd[nka + ia] = pd;
+      }
+      __syncthreads();
+      if (threadIdx.x < 4) {
+        const int kc = threadIdx.x, lo = (kc & 1) ? g.ka : 0, hi = (kc & 1) ? nka : g.ka;
+        double sacc = 0.0;
+        for (int ia = lo; ia < hi; ++ia) sacc = sacc + s_cd[(kc >= 2 ? nka : 0) + ia];
+        A.pntot[c * 4 + kc] = sacc;
+      }
+    }
+    // the advected (or equilibrated) spectrum goes back once
     if ((ntile & 1) == 0) {
       const double2 *s2 = reinterpret_cast<const double2 *>(s_ffk);
       double2 *d2 = reinterpret_cast<double2 *>(ffk);
       for (int i = threadIdx.x; i < (ntile >> 1); i += blockDim.x) d2[i] = s2[i];
     } else {
       for (int i = threadIdx.x; i < ntile; i += blockDim.x) ffk[i] = s_ffk[i];
-    }
-    if (threadIdx.x == 0) {
-      to_a[c] = to;
-      xm1o_a[c] = xm1o;
-      if (status) status[c] = st;
     }
   }
 }
@@ -306,6 +443,8 @@ struct GridCache {
   std::vector<double> host;   // concatenated copy for change detection
   double *d = nullptr;        // device copy, same concatenation
   size_t cap = 0;
+  std::vector<int> kw;
+  int *d_kw = nullptr;
 };
 GridCache g_cache[16];
 struct Scratch { char *p = nullptr; size_t bytes = 0; };
@@ -337,21 +476,30 @@ size_t smem_bytes(const mistra_kon_grid *g)
   return sizeof(double) * (5 * ntile + g->nka + g->nkt + MB + 2) + sizeof(int) * (2 + g->nka + 2);
 }
 
-int grid_to_device(const mistra_kon_grid *g, cudaStream_t st, KonGridDev *out, GridCache **cache)
+int grid_to_device(const mistra_kon_grid *g, cudaStream_t st, KonGridDev *out, GridCache **cache, bool full)
 {
+  if (full) {
+    if (!g->kw || !g->rq) return mistra_internal_fail(MISTRA_KPP_EINVAL, "mistra_kon_layers needs grid kw and rq");
+    if (g->ka < 0 || g->ka > g->nka) return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad ka");
+    for (int i = 0; i < g->nka; ++i)
+      if (g->kw[i] < 0 || g->kw[i] > g->nkt) return mistra_internal_fail(MISTRA_KPP_EINVAL, "kw out of range");
+  }
   int dev = -1;
   CKK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 16) return mistra_internal_fail(MISTRA_KPP_ENODEVICE, "device index out of range");
   GridCache &gc = g_cache[dev];
   const size_t nka = g->nka, nkt = g->nkt;
-  const size_t n_all = 3 * nka + 3 * nkt + nka * nkt + (size_t)MISTRA_JPTAERRAD * nka * nkt * MB;
+  const size_t n_all = 3 * nka + 3 * nkt + 2 * nka * nkt + (size_t)MISTRA_JPTAERRAD * nka * nkt * MB;
   std::vector<double> h;
   h.reserve(n_all);
   auto put = [&](const double *p, size_t n) { h.insert(h.end(), p, p + n); };
   put(g->en, nka); put(g->rn, nka); put(g->b0m, nka); put(g->ew, nkt); put(g->e, nkt); put(g->dew, nkt);
   put(g->rw, nka * nkt); put(g->qabs, (size_t)MISTRA_JPTAERRAD * nka * nkt * MB);
+  if (g->rq) put(g->rq, nka * nkt); else h.insert(h.end(), nka * nkt, 0.0);
+  std::vector<int> kwv(nka, 0);
+  if (g->kw) kwv.assign(g->kw, g->kw + nka);
   const bool same = gc.valid && gc.nka == g->nka && gc.nkt == g->nkt && gc.host.size() == h.size() &&
-                    !memcmp(gc.host.data(), h.data(), sizeof(double) * h.size());
+                    !memcmp(gc.host.data(), h.data(), sizeof(double) * h.size()) && gc.kw == kwv;
   if (!same) {
     if (!gc.num_sm) {
       cudaDeviceProp p;
@@ -365,10 +513,13 @@ int grid_to_device(const mistra_kon_grid *g, cudaStream_t st, KonGridDev *out, G
       CKK(cudaMalloc(&gc.d, sizeof(double) * h.size()));
       gc.cap = h.size();
     }
+    if (!gc.d_kw) CKK(cudaMalloc(&gc.d_kw, sizeof(int) * MAXK));
     gc.host.swap(h);
+    gc.kw.swap(kwv);
     gc.nka = g->nka;
     gc.nkt = g->nkt;
     CKK(cudaMemcpyAsync(gc.d, gc.host.data(), sizeof(double) * gc.host.size(), cudaMemcpyHostToDevice, st));
+    CKK(cudaMemcpyAsync(gc.d_kw, gc.kw.data(), sizeof(int) * nka, cudaMemcpyHostToDevice, st));
     CKK(cudaStreamSynchronize(st));
     gc.valid = true;
   }
@@ -380,8 +531,31 @@ int grid_to_device(const mistra_kon_grid *g, cudaStream_t st, KonGridDev *out, G
   out->nka = g->nka; out->nkt = g->nkt; out->a0m = g->a0m; out->dlne = g->dlne;
   out->en = p; p += nka; out->rn = p; p += nka; out->b0m = p; p += nka;
   out->ew = p; p += nkt; out->e = p; p += nkt; out->dew = p; p += nkt;
-  out->rw = p; p += nka * nkt; out->qabs = p;
+  out->rw = p; p += nka * nkt; out->qabs = p; p += (size_t)MISTRA_JPTAERRAD * nka * nkt * MB;
+  out->rq = p;
+  out->kw = gc.d_kw;
+  out->ka = g->ka;
   *cache = &gc;
+  return 0;
+}
+
+int launch(const mistra_kon_grid *g, int64_t ncell, double dt, const KonArgs &A, void *stream)
+{
+  const size_t smem = smem_bytes(g);
+  if (smem > 227 * 1024) return mistra_internal_fail(MISTRA_KPP_EINVAL, "grid too large for shared memory");
+  std::lock_guard<std::mutex> lk(g_mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  KonGridDev gd;
+  GridCache *gc;
+  int rc;
+  if ((rc = grid_to_device(g, st, &gd, &gc, A.full != 0))) return rc;
+  int per_sm = (int)((227 * 1024) / smem);
+  if (per_sm < 1) per_sm = 1;
+  long long blocks = (long long)gc->num_sm * per_sm;
+  if (blocks > ncell) blocks = ncell;
+  kon_subkon_kernel<<<(int)blocks, KON_THREADS, smem, st>>>(gd, ncell, dt, A);
+  CKK(cudaGetLastError());
+  g_launches.fetch_add(1);
   return 0;
 }
 
@@ -402,22 +576,11 @@ int mistra_kon_subkon_device(const mistra_kon_grid *g, int64_t ncell, double dt,
   if (ncell == 0) return 0;
   if (!d_ffk || !d_totr || !d_dfdt || !d_feualt || !d_pp || !d_to || !d_tn || !d_xm1o || !d_xm1n || !d_kr)
     return mistra_internal_fail(MISTRA_KPP_EINVAL, "null array");
-  const size_t smem = smem_bytes(g);
-  if (smem > 227 * 1024) return mistra_internal_fail(MISTRA_KPP_EINVAL, "grid too large for shared memory");
-  std::lock_guard<std::mutex> lk(g_mu);
-  cudaStream_t st = (cudaStream_t)stream;
-  KonGridDev gd;
-  GridCache *gc;
-  if ((rc = grid_to_device(g, st, &gd, &gc))) return rc;
-  int per_sm = (int)((227 * 1024) / smem);
-  if (per_sm < 1) per_sm = 1;
-  long long blocks = (long long)gc->num_sm * per_sm;
-  if (blocks > ncell) blocks = ncell;
-  kon_subkon_kernel<<<(int)blocks, KON_THREADS, smem, st>>>(gd, ncell, dt, d_ffk, d_totr, d_dfdt, d_feualt, d_pp,
-                                                           d_to, d_tn, d_xm1o, d_xm1n, d_kr, d_status);
-  CKK(cudaGetLastError());
-  g_launches.fetch_add(1);
-  return 0;
+  KonArgs A;
+  memset(&A, 0, sizeof A);
+  A.ff = d_ffk; A.totr = d_totr; A.pp = d_pp; A.kr = d_kr; A.status = d_status;
+  A.dfdt = d_dfdt; A.feualt = d_feualt; A.tn = d_tn; A.xm1n = d_xm1n; A.to = d_to; A.xm1o = d_xm1o;
+  return launch(g, ncell, dt, A, stream);
 }
 
 int mistra_kon_subkon(const mistra_kon_grid *g, int64_t ncell, double dt, double *ffk,
@@ -462,6 +625,87 @@ int mistra_kon_subkon(const mistra_kon_grid *g, int64_t ncell, double dt, double
   CKK(cudaMemcpyAsync(to, d_s[3], b_s, cudaMemcpyDeviceToHost, st));
   CKK(cudaMemcpyAsync(xm1o, d_s[5], b_s, cudaMemcpyDeviceToHost, st));
   if (status) CKK(cudaMemcpyAsync(status, d_st, b_i, cudaMemcpyDeviceToHost, st));
+  CKK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int mistra_kon_layers_device(const mistra_kon_grid *g, int64_t ncell, double dt, int chem,
+                             const mistra_kon_state *s, void *stream)
+{
+  int rc = check_grid(g);
+  if (rc) return rc;
+  if (ncell < 0) return mistra_internal_fail(MISTRA_KPP_EINVAL, "ncell < 0");
+  if (!(dt > 0.0)) return mistra_internal_fail(MISTRA_KPP_EINVAL, "dt <= 0");
+  if (ncell == 0) return 0;
+  if (!s || !s->ff || !s->t || !s->talt || !s->xm1 || !s->xm1a || !s->feu || !s->dfddt || !s->xm2 || !s->dtcon ||
+      !s->p || !s->totrad || !s->nar)
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "null array");
+  if (chem && (!s->vol1_a || !s->vol1_d || !s->part_o_a || !s->part_o_d || !s->part_n_a || !s->part_n_d ||
+               !s->vol2 || !s->pntot))
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "chem: null sum array");
+  KonArgs A;
+  memset(&A, 0, sizeof A);
+  A.full = 1; A.chem = chem ? 1 : 0;
+  A.ff = s->ff; A.totr = s->totrad; A.pp = s->p; A.kr = s->nar; A.status = s->status;
+  A.t = s->t; A.talt = s->talt; A.xm1 = s->xm1; A.xm1a = s->xm1a; A.feu = s->feu; A.dfddt = s->dfddt;
+  A.xm2 = s->xm2; A.dtcon = s->dtcon;
+  A.vol1_a = s->vol1_a; A.vol1_d = s->vol1_d; A.part_o_a = s->part_o_a; A.part_o_d = s->part_o_d;
+  A.part_n_a = s->part_n_a; A.part_n_d = s->part_n_d; A.vol2 = s->vol2; A.pntot = s->pntot;
+  return launch(g, ncell, dt, A, stream);
+}
+
+int mistra_kon_layers(const mistra_kon_grid *g, int64_t ncell, double dt, int chem,
+                      const mistra_kon_state *s, void *stream)
+{
+  int rc = check_grid(g);
+  if (rc) return rc;
+  if (ncell < 0) return mistra_internal_fail(MISTRA_KPP_EINVAL, "ncell < 0");
+  if (ncell == 0) return 0;
+  if (!s) return mistra_internal_fail(MISTRA_KPP_EINVAL, "null state");
+  int dev = -1;
+  CKK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return mistra_internal_fail(MISTRA_KPP_ENODEVICE, "device index out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)ncell, nka = g->nka, b_ff = n * nka * g->nkt * 8, b_s = n * 8;
+  // staging plan: (host pointer, bytes, copy in, copy out)
+  struct Item { void *h; size_t bytes; bool in, out; void **slot; };
+  mistra_kon_state d = *s;
+  std::vector<Item> items = {
+      {s->ff, b_ff, true, true, (void **)&d.ff}, {s->t, b_s, true, true, (void **)&d.t},
+      {s->talt, b_s, true, true, (void **)&d.talt}, {s->xm1, b_s, true, true, (void **)&d.xm1},
+      {s->xm1a, b_s, true, true, (void **)&d.xm1a}, {s->feu, b_s, true, true, (void **)&d.feu},
+      {s->dfddt, b_s, true, true, (void **)&d.dfddt}, {s->xm2, b_s, true, true, (void **)&d.xm2},
+      {s->dtcon, b_s, true, true, (void **)&d.dtcon}, {(void *)s->p, b_s, true, false, (void **)&d.p},
+      {(void *)s->totrad, n * MB * 8, true, false, (void **)&d.totrad},
+      {(void *)s->nar, n * 4, true, false, (void **)&d.nar},
+      {s->status, n * 4, false, true, (void **)&d.status}};
+  if (chem) {
+    void **sl[6] = {(void **)&d.vol1_a, (void **)&d.vol1_d, (void **)&d.part_o_a, (void **)&d.part_o_d,
+                    (void **)&d.part_n_a, (void **)&d.part_n_d};
+    double *hp[6] = {s->vol1_a, s->vol1_d, s->part_o_a, s->part_o_d, s->part_n_a, s->part_n_d};
+    for (int i = 0; i < 6; ++i) items.push_back({hp[i], n * nka * 8, false, true, sl[i]});
+    items.push_back({s->vol2, n * 4 * 8, false, true, (void **)&d.vol2});
+    items.push_back({s->pntot, n * 4 * 8, false, true, (void **)&d.pntot});
+  }
+  size_t total = 0;
+  for (auto &it : items)
+    if (it.h) total += (it.bytes + 255) & ~(size_t)255;
+  Scratch &sc = g_scratch[dev];
+  if (sc.bytes < total) {
+    if (sc.p) { CKK(cudaDeviceSynchronize()); cudaFree(sc.p); sc.p = nullptr; sc.bytes = 0; }
+    CKK(cudaMalloc(&sc.p, total));
+    sc.bytes = total;
+  }
+  char *p = sc.p;
+  for (auto &it : items) {
+    if (!it.h) { *it.slot = nullptr; continue; }
+    *it.slot = p;
+    if (it.in) CKK(cudaMemcpyAsync(p, it.h, it.bytes, cudaMemcpyHostToDevice, st));
+    p += (it.bytes + 255) & ~(size_t)255;
+  }
+  if ((rc = mistra_kon_layers_device(g, ncell, dt, chem, &d, stream))) return rc;
+  for (auto &it : items)
+    if (it.h && it.out) CKK(cudaMemcpyAsync(it.h, *it.slot, it.bytes, cudaMemcpyDeviceToHost, st));
   CKK(cudaStreamSynchronize(st));
   return 0;
 }

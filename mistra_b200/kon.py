@@ -20,7 +20,18 @@ RHOW = 1000.0
 
 class KonGrid(C.Structure):
     _fields_ = [("nka", C.c_int32), ("nkt", C.c_int32), ("a0m", C.c_double), ("dlne", C.c_double)] + [
-        (n, C.POINTER(C.c_double)) for n in ("en", "rn", "b0m", "ew", "e", "dew", "rw", "qabs")]
+        (n, C.POINTER(C.c_double)) for n in ("en", "rn", "b0m", "ew", "e", "dew", "rw", "qabs")] + [
+        ("kw", C.POINTER(C.c_int32)), ("rq", C.POINTER(C.c_double)), ("ka", C.c_int32), ("reserved", C.c_int32)]
+
+
+STATE_D = ("ff", "t", "talt", "xm1", "xm1a", "feu", "dfddt", "xm2", "dtcon", "p", "totrad")
+SUMS = ("vol1_a", "vol1_d", "part_o_a", "part_o_d", "part_n_a", "part_n_d", "vol2", "pntot")
+
+
+class KonState(C.Structure):
+    """mistra_kon_state (include/mistra_kon.h)."""
+    _fields_ = [(n, C.POINTER(C.c_double)) for n in STATE_D] + [("nar", C.POINTER(C.c_int32))] + [
+        (n, C.POINTER(C.c_double)) for n in SUMS] + [("status", C.POINTER(C.c_int32))]
 
 
 def kon_grid(rnw0=0.005, rnw1=15.0, rw0=0.005, rw1=150.0, nka=70, nkt=70, seed=7):
@@ -45,8 +56,11 @@ def kon_grid(rnw0=0.005, rnw1=15.0, rw0=0.005, rw1=150.0, nka=70, nkt=70, seed=7
 def _grid_struct(g):
     keep = [np.ascontiguousarray(g[n], dtype=np.float64) for n in ("en", "rn", "b0m", "ew", "e", "dew", "rw", "qabs")]
     assert keep[6].shape == (g["nka"], g["nkt"]) and keep[7].shape == (JPTAERRAD, g["nka"], g["nkt"], MB)
-    s = KonGrid(g["nka"], g["nkt"], g["a0m"], g["dlne"], *[a.ctypes.data_as(C.POINTER(C.c_double)) for a in keep])
-    return s, keep
+    kw = np.ascontiguousarray(g["kw"], dtype=np.int32)
+    rq = np.ascontiguousarray(g["rq"], dtype=np.float64)
+    s = KonGrid(g["nka"], g["nkt"], g["a0m"], g["dlne"], *[a.ctypes.data_as(C.POINTER(C.c_double)) for a in keep],
+                kw.ctypes.data_as(C.POINTER(C.c_int32)), rq.ctypes.data_as(C.POINTER(C.c_double)), g["ka"], 0)
+    return s, keep + [kw, rq]
 
 
 def _lib(strict=False):
@@ -93,6 +107,44 @@ def subkon_device(g, dt, ffk, totr, dfdt, feualt, pp, to, tn, xm1o, xm1n, kr, st
     _kpp._check(L, L.mistra_kon_subkon_device(C.byref(gs), C.c_int64(ffk.shape[0]), C.c_double(dt), vp(ffk), vp(totr),
                                               vp(dfdt), vp(feualt), vp(pp), vp(to), vp(tn), vp(xm1o), vp(xm1n),
                                               vp(kr), vp(status), C.c_void_p(stream)))
+
+
+def layers(g, dt, chem, st):
+    """The layer loop of SUBROUTINE kon (str.f90:4615-4772) for a batch of layers held in HOST
+    numpy arrays: `st` is a dict with ff, t, talt, xm1, xm1a, feu, dfddt, p, totrad, nar (not
+    modified).  Returns a dict with the updated arrays plus xm2, dtcon, status and, with chem,
+    vol1_a/d, part_o_a/d, part_n_a/d, vol2, pntot."""
+    L = _lib()
+    gs, keep = _grid_struct(g)
+    n = st["ff"].shape[0]
+    nka = g["nka"]
+    o = {k: np.ascontiguousarray(st[k], dtype=np.float64).copy() for k in ("ff", "t", "talt", "xm1", "xm1a", "feu",
+                                                                          "dfddt", "p", "totrad")}
+    o["xm2"] = np.zeros(n); o["dtcon"] = np.zeros(n)
+    o["nar"] = np.ascontiguousarray(st["nar"], dtype=np.int32)
+    for k in SUMS[:6]:
+        o[k] = np.zeros((n, nka))
+    o["vol2"] = np.zeros((n, 4)); o["pntot"] = np.zeros((n, 4))
+    o["status"] = np.zeros(n, dtype=np.int32)
+    s = KonState(*[_dp(o[k]) for k in STATE_D], o["nar"].ctypes.data_as(C.POINTER(C.c_int32)),
+                 *[(_dp(o[k]) if chem else None) for k in SUMS], o["status"].ctypes.data_as(C.POINTER(C.c_int32)))
+    _kpp._check(L, L.mistra_kon_layers(C.byref(gs), C.c_int64(n), C.c_double(dt), C.c_int(1 if chem else 0),
+                                       C.byref(s), None))
+    return o
+
+
+def synthetic_columns(g, ncell, seed=20261018, dry_fraction=0.3):
+    """Inputs of the kon layer loop: the humid layers of synthetic_layers plus a share of
+    dry layers (relative humidity 0.3..0.7, which take the Koehler-equilibrium branch)."""
+    d = synthetic_layers(g, ncell, seed=seed)
+    r = np.random.default_rng(seed + 1)
+    dry = r.uniform(size=ncell) < dry_fraction
+    rh = np.where(dry, r.uniform(0.3, 0.699, ncell), d["feualt"])
+    es = p21(d["to"])
+    xm1 = 0.62198 * rh * es / (d["pp"] - 0.37802 * rh * es)
+    return {"ff": d["ffk"], "t": np.where(dry, d["to"], d["tn"]), "talt": d["to"],
+            "xm1": np.where(dry, xm1, d["xm1n"]), "xm1a": np.where(dry, xm1, d["xm1o"]), "feu": rh,
+            "dfddt": d["dfdt"], "p": d["pp"], "totrad": d["totr"], "nar": d["kr"]}
 
 
 def launch_count():

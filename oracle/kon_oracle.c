@@ -30,6 +30,9 @@ typedef struct {
   const double *ew, *e, *dew;   /* [nkt] */
   const double *rw;             /* [nka][nkt] */
   const double *qabs;           /* [3][nka][nkt][18] */
+  const int *kw;                /* [nka] (layers only) */
+  const double *rq;             /* [nka][nkt] (layers only) */
+  int ka, reserved;
 } kon_grid;
 
 /* constants.f90:48-83 */
@@ -215,5 +218,108 @@ void kon_oracle_subkon(const kon_grid *g, int64_t ncell, double dt, double *ffk_
     to_a[c] = to;
     xm1o_a[c] = xm1o;
     status[c] = st;
+  }
+}
+
+/* FUNCTION rgl (str.f90:2164-2251): Koehler equilibrium radius by Newton iteration */
+static double rgl(double r_dry, double a, double b, double feu)
+{
+  if (feu >= 1.0) return r_dry;
+  const double zlogf = log(feu);
+  const double alpha = a / r_dry;
+  double xalt = exp(feu), xneu = xalt;
+  for (int ij = 1; ij <= 100; ++ij) {
+    const double falt = (xalt * xalt * xalt - 1.0) * (xalt * zlogf - alpha) + b * xalt;
+    const double fstralt = (4.0 * (xalt * xalt * xalt) - 1.0) * zlogf - 3.0 * (xalt * xalt) * alpha + b;
+    xneu = xalt - falt / fstralt;
+    if (fabs(xneu - xalt) < 1.e-7 * xalt) break;
+    xalt = xneu;
+  }
+  return r_dry * xneu;
+}
+
+typedef struct {
+  double *ff, *t, *talt, *xm1, *xm1a, *feu, *dfddt, *xm2, *dtcon;
+  const double *p, *totrad;
+  const int32_t *nar;
+  double *vol1_a, *vol1_d, *part_o_a, *part_o_d, *part_n_a, *part_n_d, *vol2, *pntot;
+  int32_t *status;
+} kon_state;
+
+/* The layer loop of SUBROUTINE kon (str.f90:4615-4772) for ncell layers: bin sums before,
+ * dry branch (feu < 0.7: SUBROUTINE equil case 1, str.f90:4801-4981) or humid branch
+ * (subkon + write-back 4708-4721), bin sums after.  status: 0 dry, else as subkon. */
+void kon_oracle_layers(const kon_grid *g, int64_t ncell, double dt, int chem, const kon_state *s)
+{
+  const int nka = g->nka, nkt = g->nkt, ka = g->ka;
+  const size_t tile = (size_t)nka * nkt;
+  const double z4pi3 = 4.0 * pi / 3.0;               /* str.f90:4560 */
+  for (int64_t c = 0; c < ncell; ++c) {
+    double *ffk = s->ff + c * tile;
+    const double tn = s->t[c], xm1n = s->xm1[c], pp = s->p[c];
+    s->dtcon[c] = 0.0;
+    if (chem) {                                      /* str.f90:4625-4659 */
+      double v2[4] = {0, 0, 0, 0};
+      for (int ia = 0; ia < nka; ++ia) {
+        double va = 0, pa = 0, vd = 0, pd = 0;
+        for (int jt = 0; jt < nkt; ++jt) {
+          const double f = ffk[ia * nkt + jt], r = g->rq[ia * nkt + jt];
+          const double v = f * z4pi3 * (r * r * r);
+          if (jt < g->kw[ia]) { va = va + v; pa = pa + f; } else { vd = vd + v; pd = pd + f; }
+        }
+        s->vol1_a[c * nka + ia] = va; s->part_o_a[c * nka + ia] = pa;
+        s->vol1_d[c * nka + ia] = vd; s->part_o_d[c * nka + ia] = pd;
+        if (ia < ka) { v2[0] = v2[0] + va; v2[2] = v2[2] + vd; } else { v2[1] = v2[1] + va; v2[3] = v2[3] + vd; }
+      }
+      for (int k = 0; k < 4; ++k) s->vol2[c * 4 + k] = v2[k];
+    }
+    if (s->feu[c] < 0.7) {                           /* str.f90:4663-4672 */
+      const double feun = xm1n * pp / ((0.62198 + 0.37802 * xm1n) * p21(tn));
+      s->feu[c] = feun;
+      const double a0 = g->a0m / tn;
+      double x2 = 0.0;
+      for (int ia = 0; ia < nka; ++ia) {             /* equil case 1 */
+        double tot = 0.0;
+        for (int jt = 0; jt < nkt; ++jt) { tot = tot + ffk[ia * nkt + jt]; ffk[ia * nkt + jt] = 0.0; }
+        const double rn = g->rn[ia];
+        const double rg = rgl(rn, a0, g->b0m[ia] * 2.0, feun);
+        const double eg = (4.e-09 * pi / 3.0) * (rg * rg * rg - rn * rn * rn);
+        int jt = 1;
+        while (jt < nkt && eg > g->ew[jt - 1]) jt = jt + 1;
+        ffk[ia * nkt + jt - 1] = tot;
+      }
+      for (int ia = 0; ia < nka; ++ia)
+        for (int jt = 0; jt < nkt; ++jt) x2 = x2 + ffk[ia * nkt + jt] * g->e[jt];
+      s->xm2[c] = x2;
+      if (s->status) s->status[c] = 0;
+    } else {                                         /* str.f90:4676-4721 */
+      double to = s->talt[c], xm1o = s->xm1a[c];
+      const double feualt = s->feu[c];
+      int32_t st, kr = s->nar[c];
+      kon_oracle_subkon(g, 1, dt, ffk, s->totrad + c * MB, &s->dfddt[c], &feualt, &pp, &to, &tn, &xm1o, &xm1n,
+                        &kr, &st);
+      s->t[c] = to; s->talt[c] = to; s->xm1[c] = xm1o; s->xm1a[c] = xm1o;
+      s->feu[c] = xm1o * pp / ((0.62198 + 0.37802 * xm1o) * p21(to));
+      s->dfddt[c] = (s->feu[c] - feualt) / dt;
+      double x2 = 0.0;
+      for (int ia = 0; ia < nka; ++ia)
+        for (int jt = 0; jt < nkt; ++jt) x2 = x2 + ffk[ia * nkt + jt] * g->e[jt];
+      s->xm2[c] = x2;
+      s->dtcon[c] = (to - tn) / dt;
+      if (s->status) s->status[c] = st;
+    }
+    if (chem) {                                      /* str.f90:4724-4770 */
+      double pn[4] = {0, 0, 0, 0};
+      for (int ia = 0; ia < nka; ++ia) {
+        double pa = 0, pd = 0;
+        for (int jt = 0; jt < nkt; ++jt) {
+          const double f = ffk[ia * nkt + jt];
+          if (jt < g->kw[ia]) pa = pa + f; else pd = pd + f;
+        }
+        s->part_n_a[c * nka + ia] = pa; s->part_n_d[c * nka + ia] = pd;
+        if (ia < ka) { pn[0] = pn[0] + pa; pn[2] = pn[2] + pd; } else { pn[1] = pn[1] + pa; pn[3] = pn[3] + pd; }
+      }
+      for (int k = 0; k < 4; ++k) s->pntot[c * 4 + k] = pn[k];
+    }
   }
 }

@@ -101,3 +101,56 @@ def test_large_batch_permutation_and_device_entry(cuda_device, kpp):
     assert kon.launch_count() == n0 + 1
     assert np.array_equal(t["ffk"].cpu().numpy(), out[0]) and np.array_equal(st.cpu().numpy(), out[3])
     assert np.array_equal(t["to"].cpu().numpy(), out[1])
+
+
+LKEYS = ("ff", "t", "talt", "xm1", "xm1a", "feu", "dfddt", "xm2", "dtcon")
+SKEYS = ("vol1_a", "vol1_d", "part_o_a", "part_o_d", "part_n_a", "part_n_d", "vol2", "pntot")
+
+
+def check_layers(o, r, chem):
+    dry = r["status"] == 0
+    same = o["status"] == r["status"]
+    assert same.mean() >= 0.99 and np.array_equal(o["status"][dry], r["status"][dry])
+    # dry branch: Newton iteration with the CUDA log/exp - same bins, same numbers
+    assert np.array_equal(o["ff"][dry], r["ff"][dry])
+    for k in ("t", "talt", "xm1", "xm1a", "dtcon"):
+        assert np.array_equal(o[k][dry], r[k][dry])
+    assert np.allclose(o["feu"][dry], r["feu"][dry], rtol=1e-14) and np.allclose(o["xm2"][dry], r["xm2"][dry], rtol=1e-13)
+    hs = same & ~dry
+    for k in ("t", "talt", "xm1", "xm1a", "feu", "xm2"):
+        assert np.allclose(o[k][hs], r[k][hs], rtol=1e-11), k
+    assert np.allclose(o["dfddt"][hs], r["dfddt"][hs], rtol=1e-6, atol=1e-12)
+    assert np.allclose(o["dtcon"][hs], r["dtcon"][hs], rtol=1e-6, atol=1e-12)
+    scale = np.abs(r["ff"]).max(axis=(1, 2), keepdims=True) + 1e-300
+    assert (np.abs(o["ff"] - r["ff"]) / scale)[hs].max() <= 1e-9
+    if chem:
+        for k in SKEYS:
+            assert np.allclose(o[k][same], r[k][same], rtol=1e-9, atol=1e-12 * np.abs(r[k]).max()), k
+
+
+@pytest.mark.parametrize("chem", [True, False])
+def test_kon_layer_loop_vs_oracle(cuda_device, kpp, chem):
+    grid = kon.kon_grid()
+    st = kon.synthetic_columns(grid, 500, seed=21, dry_fraction=0.35)
+    r = ko.layers(grid, 10.0, chem, st)
+    o = kon.layers(grid, 10.0, chem, st)
+    check_layers(o, r, chem)
+    assert (r["status"] == 0).sum() > 100 and (r["status"] >= 1).sum() > 200
+    if not chem:
+        assert not o["vol2"].any()
+
+
+def test_kon_layer_loop_edges(cuda_device, kpp):
+    grid = kon.kon_grid(0.01, 2.0, 0.01, 80.0)                                # BTZ96 grid
+    st = kon.synthetic_columns(grid, 40, seed=22, dry_fraction=0.5)
+    st["ff"][3] = 0.0                                                         # empty layers, dry and humid
+    st["feu"][4] = 0.6999999; st["feu"][5] = 0.7                             # either side of the branch
+    r = ko.layers(grid, 10.0, True, st)
+    o = kon.layers(grid, 10.0, True, st)
+    check_layers(o, r, True)
+    assert r["status"][4] == 0 and r["status"][5] != 0
+    e = {k: v[:0] for k, v in st.items()}
+    assert kon.layers(grid, 10.0, True, e)["ff"].shape[0] == 0
+    bad = dict(grid); bad["kw"] = grid["kw"] + 1000
+    with pytest.raises(kpp.KppError):
+        kon.layers(bad, 10.0, True, st)

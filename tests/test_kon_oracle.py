@@ -94,3 +94,52 @@ def test_subkon_empty_layer_and_golden(grid):
     assert np.array_equal(st, gd["status"])
     assert np.allclose(ffk, gd["ffk_out"], rtol=1e-12, atol=1e-14 * gd["ffk_out"].max())
     assert np.allclose(to, gd["to_out"], rtol=1e-14) and np.allclose(xm1o, gd["xm1o_out"], rtol=1e-13)
+
+
+def test_layers_dry_branch_is_koehler_equilibrium(grid):
+    """kon's layer loop (str.f90:4615-4772): dry layers (feu < 0.7) go through equil."""
+    st = kon.synthetic_columns(grid, 64, seed=8, dry_fraction=0.5)
+    o = ko.layers(grid, 10.0, True, st)
+    dry = st["feu"] < 0.7
+    assert (o["status"][dry] == 0).all() and (o["status"][~dry] >= 1).all()
+    ff = o["ff"]
+    # every dry class sits in exactly one water bin and keeps its particles
+    assert np.allclose(ff.sum(axis=2), st["ff"].sum(axis=2), rtol=1e-13, atol=1e-300)
+    occupied = (ff[dry] > 0).sum(axis=2)
+    assert (occupied <= 1).all()
+    # that bin brackets the equilibrium water mass: ew(jt-1) < eg <= ew(jt), with rg from the
+    # Koehler equation  ln(feu) = a0/rg - b0*rn^3/(rg^3 - rn^3)
+    k = np.nonzero(dry)[0][0]
+    feun = st["xm1"][k] * st["p"][k] / ((0.62198 + 0.37802 * st["xm1"][k]) * kon.p21(st["t"][k]))
+    assert np.isclose(o["feu"][k], feun, rtol=1e-14)
+    a0 = grid["a0m"] / st["t"][k]
+    for ia in (5, 30, 60):
+        jt = int(np.argmax(ff[k, ia] > 0))
+        lo = grid["ew"][jt - 1] if jt > 0 else 0.0
+        # solve the Koehler equation independently by bisection on the water mass
+        rn = grid["rn"][ia]
+        f = lambda rg: np.log(feun) - (a0 / rg - 2.0 * grid["b0m"][ia] * rn ** 3 / (rg ** 3 - rn ** 3))
+        a, b = rn * (1 + 1e-9), rn * 50
+        for _ in range(200):
+            m = 0.5 * (a + b)
+            a, b = (m, b) if f(m) > 0 else (a, m)          # f falls from +inf (rg -> rn) through 0
+        eg = 4.0e-9 * np.pi / 3.0 * (a ** 3 - rn ** 3)
+        assert lo * (1 - 1e-6) <= eg <= grid["ew"][jt] * (1 + 1e-6)
+    # untouched in the dry branch: temperature and vapour; dtcon = 0
+    assert np.array_equal(o["t"][dry], st["t"][dry]) and np.array_equal(o["xm1"][dry], st["xm1"][dry])
+    assert not o["dtcon"][dry].any()
+    # humid layers are exactly subkon + the write-back of str.f90:4708-4721
+    i = np.nonzero(~dry)[0]
+    f2, to, xm1o, s2 = ko.subkon(grid, 10.0, st["ff"][i], st["totrad"][i], st["dfddt"][i], st["feu"][i], st["p"][i],
+                                 st["talt"][i], st["t"][i], st["xm1a"][i], st["xm1"][i], st["nar"][i])
+    assert np.array_equal(f2, ff[i]) and np.array_equal(to, o["t"][i]) and np.array_equal(to, o["talt"][i])
+    assert np.array_equal(xm1o, o["xm1"][i]) and np.array_equal(s2, o["status"][i])
+    assert np.allclose(o["dtcon"][i], (to - st["t"][i]) / 10.0, rtol=0, atol=0)
+    assert np.allclose(o["xm2"], (ff * grid["e"][None, None, :]).sum(axis=(1, 2)), rtol=1e-12)
+    # bin sums for konc
+    kw, ka = grid["kw"], grid["ka"]
+    aer = np.arange(grid["nkt"])[None, :] < kw[:, None]
+    assert np.allclose(o["part_o_a"], (st["ff"] * aer[None]).sum(axis=2), rtol=1e-13, atol=1e-300)
+    assert np.allclose(o["part_n_d"], (ff * ~aer[None]).sum(axis=2), rtol=1e-13, atol=1e-300)
+    assert np.allclose(o["pntot"][:, 0], o["part_n_a"][:, :ka].sum(axis=1), rtol=1e-13)
+    assert np.allclose(o["vol2"][:, 3], o["vol1_d"][:, ka:].sum(axis=1), rtol=1e-13)
