@@ -29,9 +29,9 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", HOSTCXX]
 
 UNITS = ["kpp_mech_g.cu", "kpp_mech_a.cu", "kpp_mech_t.cu", "kpp_api.cu", "bins_kernels.cu",
-         "kon_kernels.cu", "_gen/kpp_names.cpp"]
+         "kon_kernels.cu", "rconst_kernels.cu", "_gen/kpp_names.cpp"]
 # per-unit flags: the condensation kernel keeps the reference's unfused arithmetic
-UNIT_FLAGS = {"kon_kernels.cu": ["-fmad=false"]}
+UNIT_FLAGS = {"kon_kernels.cu": ["-fmad=false"], "rconst_kernels.cu": ["-fmad=false"]}
 
 
 def _hash(paths, extra):
@@ -50,6 +50,10 @@ def _deps(unit):
         deps.append(os.path.join(ROOT, "include", "mistra_bins.h"))
     if unit.startswith("kon_"):
         deps.append(os.path.join(ROOT, "include", "mistra_kon.h"))
+    if unit.startswith("rconst_"):
+        deps += [os.path.join(ROOT, "include", "mistra_rconst.h"), os.path.join(ROOT, "include", "mistra_rconst_cuda.h"),
+                 os.path.join(CSRC, "rate_laws.h"), os.path.join(CSRC, "rconst_common.h")]
+        deps += [os.path.join(CSRC, "_gen", "rconst_%s.inc" % x) for x in "gat"]
     if unit.startswith("kpp_mech_"):
         x = unit[len("kpp_mech_")]
         deps += [os.path.join(CSRC, "_gen", "mech_%s.cuh" % x), os.path.join(CSRC, "ros3_kernel.inc")]
@@ -145,7 +149,8 @@ def build_rconst(verbose=False):
     """Host-side Update_RCONST_x producer (include/mistra_rconst.h), plain g++."""
     so = os.path.join(HERE, "libmistra_rconst.so")
     srcs = [os.path.join(CSRC, "rconst_host.cpp"), os.path.join(CSRC, "_gen", "kpp_names.cpp")]
-    deps = srcs + [os.path.join(CSRC, "rate_laws.h"), os.path.join(ROOT, "include", "mistra_rconst.h")] + [
+    deps = srcs + [os.path.join(CSRC, "rate_laws.h"), os.path.join(CSRC, "rconst_common.h"),
+                   os.path.join(ROOT, "include", "mistra_rconst.h")] + [
         os.path.join(CSRC, "_gen", "rconst_%s.inc" % x) for x in "gat"]
     hv = _hash(deps, HOSTCXX)
     stamp = os.path.join(OBJ, "rconst.sha")

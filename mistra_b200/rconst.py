@@ -80,3 +80,36 @@ def update_rconst(mech, cb1, scal, ph_rat, conc, yhenry=None, yxkmt=None, ykef=N
     if rc != 0:
         raise ValueError("mistra_rconst_update failed (%d)" % rc)
     return out
+
+
+def update_rconst_device(mech, cb1, scal, ph_rat, conc, out=None, yhenry=None, yxkmt=None, ykef=None, ykeb=None,
+                         yxkmtd=None, yxeq=None, ycw=None, ycwd=None, f32_literals=1, stream=None):
+    """Update_RCONST_x on the device (include/mistra_rconst_cuda.h): all arrays are contiguous
+    float64 CUDA tensors on the current device, one row per cell; returns the [ncell][NREACT]
+    tensor (`out` if given).  Asynchronous on torch's current stream."""
+    import torch
+    from . import kpp
+    L = kpp.library()
+    L.mistra_rconst_update_device.argtypes = [C.c_int, C.POINTER(RateInputs), C.c_void_p, C.c_void_p]
+    m = mechmod.load(mechmod.MECH_NAMES[mech])
+    nspec, nkc, n = m.nvar + m.nfix, NKC[mech], conc.shape[0]
+
+    def ptr(t, shape):
+        if t is None:
+            return None
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float64 and tuple(t.shape) == shape):
+            raise ValueError("update_rconst_device: need contiguous CUDA float64 %s, got %s" % (shape, tuple(t.shape)))
+        return C.cast(t.data_ptr(), C.POINTER(C.c_double))
+    ri = RateInputs()
+    ri.ncell = n
+    ri.cb1 = ptr(cb1, (n, 4)); ri.scal = ptr(scal, (n, 13)); ri.ph_rat = ptr(ph_rat, (n, NPHRXN))
+    ri.conc = ptr(conc, (n, nspec)); ri.yhenry = ptr(yhenry, (n, nspec)); ri.yxkmt = ptr(yxkmt, (n, nkc, nspec))
+    ri.ykef = ptr(ykef, (n, nkc, nspec)); ri.ykeb = ptr(ykeb, (n, nkc, nspec)); ri.yxkmtd = ptr(yxkmtd, (n, 2, nspec))
+    ri.yxeq = ptr(yxeq, (n, nspec)); ri.ycw = ptr(ycw, (n, nkc)); ri.ycwd = ptr(ycwd, (n, 2))
+    ri.f32_literals = int(f32_literals)
+    if out is None:
+        out = torch.empty((n, m.nreact), dtype=torch.float64, device=conc.device)
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    kpp._check(L, L.mistra_rconst_update_device(mech, C.byref(ri), C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
+    return out
