@@ -20,3 +20,13 @@ const KppMechInfo *kpp_mech_info_a()
                                    (const void *)ros3_kernel_a, ros3_launch_a, set_coef};
   return &info;
 }
+
+#ifdef KPP_PHASE_TIMERS
+extern "C" int mistra_kpp_phase_a(unsigned long long *out, int reset)
+{
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(out, mech_a::g_phase, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(mech_a::g_phase, z, sizeof z); }
+  return (int)e;
+}
+#endif

@@ -20,3 +20,13 @@ const KppMechInfo *kpp_mech_info_g()
                                    (const void *)ros3_kernel_g, ros3_launch_g, set_coef};
   return &info;
 }
+
+#ifdef KPP_PHASE_TIMERS
+extern "C" int mistra_kpp_phase_g(unsigned long long *out, int reset)
+{
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(out, mech_g::g_phase, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(mech_g::g_phase, z, sizeof z); }
+  return (int)e;
+}
+#endif
