@@ -7,11 +7,15 @@
 // layer (196 kB for 70 x 70, one CTA per SM): the growth-rate coefficients cd, cr, sr (set
 // up once by all threads, 18-band radiative sum from the L2-resident qabs table), the
 // spectrum before the step falt (cp.async from HBM) and the advected spectrum ffk (written
-// back once).  Per secant iteration one thread per dry class ia advects its row along the
-// water-mass axis exactly as advec does (sequential in i, scatter into k_low/k_high), the
-// advection velocities u(k) are evaluated on the fly from cd, cr, sr; the liquid-water
-// change is summed per row, then over rows by one thread, which also runs the secant
-// update.  Compiled without FMA contraction (build.py) so that the arithmetic is the
+// back once).  Per secant iteration the advection of advec is split in two: (A) one thread per
+// grid point (ia, i) walks the Courant path of that bin and evaluates Bott's polynomial flux
+// (the expensive, independent part: divisions, u(k) from cd, cr, sr on the fly) and parks
+// the target bin and the flux x1 in shared memory; (B) one thread per target bin (ia, k) adds
+// the contributions that land on y(k) in increasing i - the order of the reference's loop - so
+// every y(k) sees the same additions in the same order and the result is the sequential one
+// to the last bit (the scan is bounded by the row's largest bin displacement).  Rows go through A/B in chunks sized by the shared memory left.  The
+// liquid-water change is summed per row, then over rows by one thread, which also runs the
+// secant update.  Compiled without FMA contraction (build.py) so that the arithmetic is the
 // reference's up to the CUDA exp/pow (<= 2 ulp) and the per-row summation of dwsum.
 #include "../../include/mistra_kon.h"
 #include "../../include/mistra_kpp.h"
@@ -29,7 +33,8 @@ int mistra_internal_fail(int code, const std::string &msg);  // kpp_api.cu
 namespace {
 
 constexpr int MB = MISTRA_MB;
-constexpr int KON_THREADS = 128;
+constexpr int KON_THREADS = 512;
+constexpr int KON_MAX_NKA = 128;
 constexpr int MAXK = 128;
 
 struct KonGridDev {
@@ -124,82 +129,125 @@ struct RowCoef {
   }
 };
 
-// SUBROUTINE advec (str.f90:5321-5516) for one row: z = spectrum before (read only),
-// y = advected spectrum (zeroed here, then scattered into).  Returns 1 where the reference
-// aborts (target bin outside the grid).
-__device__ int advec_row(int nkt, double dt, const RowCoef &rc, const double *__restrict__ z,
-                         double *__restrict__ y)
+// SUBROUTINE advec (str.f90:5321-5516), part A for one source bin i (1-based) of a row:
+// z = spectrum before (read only).  Returns the kind of contribution in the high byte and
+// the target bin (1-based) in the low byte; *x1 = flux into k_low+1 for ADV_SPLIT.
+enum { ADV_SKIP = 0, ADV_ADD = 1, ADV_SPLIT = 2, ADV_ERR = 3 };
+__device__ __forceinline__ unsigned advec_flux(int nkt, double dt, const RowCoef &rc, const double *__restrict__ z,
+                                               int i, double *x1_out)
 {
   const double ymin = 1.e-32;
-  for (int i = 0; i < nkt; ++i) y[i] = 0.0;
-  int i0 = 1;
-  while (z[i0 - 1] < ymin) {
-    if (i0 == nkt) return 0;
-    i0 = i0 + 1;
-  }
-  int i1 = nkt;
-  while (z[i1 - 1] < ymin) i1 = i1 - 1;
-  for (int i = i0; i <= i1; ++i) {
-    const double zi = z[i - 1];
-    if (zi < ymin) continue;
-    int k2 = 0, k1, k = i;
-    double dt0, dt1 = dt, x0;
-    double uk = rc.u(k);
+  const double zi = z[i - 1];
+  if (zi < ymin) return ADV_SKIP << 8;
+  int k2 = 0, k1, k = i;
+  double dt0, dt1 = dt, x0;
+  double uk = rc.u(k);
+  if (fabs(uk) > 0.0) dt0 = fmin(1.0 / fabs(uk), dt1);
+  else return (ADV_ADD << 8) | (unsigned)k;
+  x0 = (double)k + uk * dt0;
+  dt1 = dt1 - dt0;
+  k1 = k;
+  while (dt1 > 1.e-7) {
+    if (uk < 0.0) k = k - 1; else k = k + 1;
+    if (k == k2) return (ADV_ADD << 8) | (unsigned)k;
+    k2 = k1;
+    k1 = k;
+    if (k < 1 || k > nkt) return ADV_ERR << 8;
+    uk = rc.u(k);
     if (fabs(uk) > 0.0) dt0 = fmin(1.0 / fabs(uk), dt1);
-    else { y[k - 1] = y[k - 1] + zi; continue; }
+    else return (ADV_ADD << 8) | (unsigned)k;
     x0 = (double)k + uk * dt0;
     dt1 = dt1 - dt0;
-    k1 = k;
-    bool done = false;
-    while (dt1 > 1.e-7) {
-      if (uk < 0.0) k = k - 1; else k = k + 1;
-      if (k == k2) { y[k - 1] = y[k - 1] + zi; done = true; break; }
-      k2 = k1;
-      k1 = k;
-      if (k < 1 || k > nkt) return 1;
-      uk = rc.u(k);
-      if (fabs(uk) > 0.0) dt0 = fmin(1.0 / fabs(uk), dt1);
-      else { y[k - 1] = y[k - 1] + zi; done = true; break; }
-      x0 = (double)k + uk * dt0;
-      dt1 = dt1 - dt0;
-    }
-    if (done) continue;
-    const int k_low = (int)floor(x0), k_high = k_low + 1;
-    const double c0 = x0 - (double)k_low;
-    if (k_low < 1 || (k_high > nkt && c0 > 0.0)) return 1;
-    if (c0 > 0.0) {
-      double x1;
-      if (i == 1 || i == nkt) {
-        x1 = c0 * zi;
-      } else if (i == 2 || i == nkt - 1) {
-        const double al = 1.0 - 2.0 * c0, al2 = al * al;
-        const double a0 = (26.0 * zi - z[i] - z[i - 2]) / 24.0;
-        const double a1 = (z[i] - z[i - 2]) / 16.0;
-        const double a2 = (z[i] + z[i - 2] - 2.0 * zi) / 48.0;
-        x1 = fmin(zi, a0 * c0 + a1 * (1.0 - al2) + a2 * (1.0 - al2 * al));
-      } else {
-        const double al = 1.0 - 2.0 * c0, al2 = al * al, al3 = al2 * al;
-        const double zp2 = z[i + 1], zp1 = z[i], zm1 = z[i - 2], zm2 = z[i - 3];
-        const double a0 = (9.0 * (zp2 + zm2) - 116.0 * (zp1 + zm1) + 2134.0 * zi) / 1920.0;
-        const double a1 = (-5.0 * (zp2 - zm2) + 34.0 * (zp1 - zm1)) / 384.0;
-        const double a2 = (-zp2 + 12.0 * (zp1 + zm1) - 22.0 * zi - zm2) / 384.0;
-        const double a3 = (zp2 - 2.0 * (zp1 - zm1) - zm2) / 768.0;
-        const double a4 = (zp2 - 4.0 * (zp1 + zm1) + 6.0 * zi + zm2) / 3840.0;
-        x1 = fmin(zi, a0 * c0 + a1 * (1.0 - al2) + a2 * (1.0 - al3) + a3 * (1.0 - al2 * al2)
-                          + a4 * (1.0 - al2 * al3));
-      }
-      x1 = fmax(0.0, x1);
-      y[k_low - 1] = y[k_low - 1] + zi - x1;
-      y[k_high - 1] = y[k_high - 1] + x1;
-    } else {
-      y[k_low - 1] = y[k_low - 1] + zi;
-    }
   }
-  return 0;
+  const int k_low = (int)floor(x0), k_high = k_low + 1;
+  const double c0 = x0 - (double)k_low;
+  if (k_low < 1 || (k_high > nkt && c0 > 0.0)) return ADV_ERR << 8;
+  if (!(c0 > 0.0)) return (ADV_ADD << 8) | (unsigned)k_low;
+  double x1;
+  if (i == 1 || i == nkt) {
+    x1 = c0 * zi;
+  } else if (i == 2 || i == nkt - 1) {
+    const double al = 1.0 - 2.0 * c0, al2 = al * al;
+    const double a0 = (26.0 * zi - z[i] - z[i - 2]) / 24.0;
+    const double a1 = (z[i] - z[i - 2]) / 16.0;
+    const double a2 = (z[i] + z[i - 2] - 2.0 * zi) / 48.0;
+    x1 = fmin(zi, a0 * c0 + a1 * (1.0 - al2) + a2 * (1.0 - al2 * al));
+  } else {
+    const double al = 1.0 - 2.0 * c0, al2 = al * al, al3 = al2 * al;
+    const double zp2 = z[i + 1], zp1 = z[i], zm1 = z[i - 2], zm2 = z[i - 3];
+    const double a0 = (9.0 * (zp2 + zm2) - 116.0 * (zp1 + zm1) + 2134.0 * zi) / 1920.0;
+    const double a1 = (-5.0 * (zp2 - zm2) + 34.0 * (zp1 - zm1)) / 384.0;
+    const double a2 = (-zp2 + 12.0 * (zp1 + zm1) - 22.0 * zi - zm2) / 384.0;
+    const double a3 = (zp2 - 2.0 * (zp1 - zm1) - zm2) / 768.0;
+    const double a4 = (zp2 - 4.0 * (zp1 + zm1) + 6.0 * zi + zm2) / 3840.0;
+    x1 = fmin(zi, a0 * c0 + a1 * (1.0 - al2) + a2 * (1.0 - al3) + a3 * (1.0 - al2 * al2)
+                      + a4 * (1.0 - al2 * al3));
+  }
+  *x1_out = fmax(0.0, x1);
+  return (ADV_SPLIT << 8) | (unsigned)k_low;
 }
 
+// Part B for one target bin k (1-based) of a row: the additions advec's loop over i makes to
+// y(k), in its order (increasing i).  Source bin i contributes to y(k_low) and, when split, to
+// y(k_low+1); `w` bounds |k_low - i| over the row, so only i in [k-1-w, k+w] can reach k;
+// `iend` = first source bin at which the reference aborts (nkt+1 if none): the sequential loop
+// never gets to the bins from there on.  y starts from 0 as in advec.
+__device__ __forceinline__ double advec_gather(int nkt, int k, int w, int iend, const double *__restrict__ z,
+                                               const double *__restrict__ x1, const unsigned short *__restrict__ code)
+{
+  double y = 0.0;
+  const int lim = min(nkt, iend - 1);
+  if (w <= 1) {
+    // usual case (Courant numbers below one bin): only i = k-2 .. k+1 can reach k; the four
+    // candidates are fetched at once, the additions keep their order
+    unsigned cd[4];
+    double zz[4], ff[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int i = k - 2 + d;
+      const bool ok = (i >= 1) && (i <= lim);
+      cd[d] = ok ? (unsigned)code[ok ? i - 1 : 0] : (unsigned)(ADV_SKIP << 8);
+      zz[d] = z[ok ? i - 1 : 0];
+      ff[d] = x1[ok ? i - 1 : 0];
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const unsigned kind = cd[d] >> 8;
+      const int kl = (int)(cd[d] & 255u);
+      if (kind == ADV_ADD) {
+        if (kl == k) y = y + zz[d];
+      } else if (kind == ADV_SPLIT) {
+        if (kl == k) y = y + zz[d] - ff[d];
+        else if (kl == k - 1) y = y + ff[d];
+      }
+    }
+    return y;
+  }
+  const int lo = max(1, k - 1 - w), hi = min(k + w, lim);
+  for (int i = lo; i <= hi; ++i) {
+    const unsigned cd = code[i - 1], kind = cd >> 8;
+    const int kl = (int)(cd & 255u);
+    if (kind == ADV_ADD) {
+      if (kl == k) y = y + z[i - 1];
+    } else if (kind == ADV_SPLIT) {
+      if (kl == k) y = y + z[i - 1] - x1[i - 1];
+      else if (kl == k - 1) y = y + x1[i - 1];
+    }
+  }
+  return y;
+}
+
+#ifdef KON_PROF
+__device__ unsigned long long g_kon_prof[8];
+#define KP_START() long long kp_prev = clock64()
+#define KP(i) { const long long kp_now = clock64(); if (threadIdx.x == 0) atomicAdd(&g_kon_prof[i], (unsigned long long)(kp_now - kp_prev)); kp_prev = kp_now; }
+#else
+#define KP_START()
+#define KP(i)
+#endif
+
 __global__ void __launch_bounds__(KON_THREADS)
-kon_subkon_kernel(KonGridDev g, long long ncell, double dt, KonArgs A)
+kon_subkon_kernel(KonGridDev g, long long ncell, double dt, KonArgs A, int rch)
 {
   double *__restrict__ ffk_all = A.ff;
   const double *__restrict__ totr_all = A.totr;
@@ -212,6 +260,10 @@ kon_subkon_kernel(KonGridDev g, long long ncell, double dt, KonArgs A)
   double *s_totr = s_e + nkt;        // [MB]
   double *s_it = s_totr + MB;        // [2] fquer, spare
   int *s_flag = (int *)(s_it + 2);   // [0] stop code, [1] advec error, [2..2+nka) kr0 switch per class
+  double *s_x1 = (double *)(s_flag + ((nka + 5) & ~1));          // [rch][nkt] flux of part A
+  unsigned short *s_code = (unsigned short *)(s_x1 + rch * nkt);   // [rch][nkt] kind << 8 | target bin
+  int *s_w = (int *)(s_code + ((rch * nkt + 1) & ~1));             // [rch] largest |k_low - i| of the row
+  int *s_iend = s_w + rch;                                         // [rch] first aborting source bin
   const double r0 = kGasConst / kMair, r1 = kGasConst / kMwat;
 
   for (int i = threadIdx.x; i < nkt; i += blockDim.x) s_e[i] = g.e[i];
@@ -224,6 +276,7 @@ kon_subkon_kernel(KonGridDev g, long long ncell, double dt, KonArgs A)
 
   for (long long c = blockIdx.x; c < ncell; c += gridDim.x) {
     __syncthreads();
+    KP_START();
     double *ffk = ffk_all + (size_t)c * ntile;
     if ((ntile & 1) == 0)
       for (int i = threadIdx.x; i < (ntile >> 1); i += blockDim.x) cp_async16(s_falt + 2 * i, ffk + 2 * i);
@@ -307,6 +360,7 @@ kon_subkon_kernel(KonGridDev g, long long ncell, double dt, KonArgs A)
     const int kr = A.kr[c];
     __syncthreads();  // s_totr visible
     const int ib0 = (s_totr[0] < 1.0) ? 7 : 1;
+    KP(0);
     // ---- growth-rate coefficients over the grid (str.f90:5128-5149) ----
     for (int q = threadIdx.x; q < ntile; q += blockDim.x) {
       const int ia = q / nkt + 1, jt = q - (ia - 1) * nkt + 1;
@@ -318,10 +372,15 @@ kon_subkon_kernel(KonGridDev g, long long ncell, double dt, KonArgs A)
       const double xkas = xka / (rk / (rk + deltat) + xka0 / rk);
       const double x1 = kRhow * (zxl21 + xkas / (xdvs * rho21s * srq));
       const int kr0 = (kr == 3 && s_flag[2 + ia - 1]) ? 2 : kr;
+      // device table: [kr][ia][ib][jt] of qabs(ib,jt)*de0 + qabs(ib,jtp)*dep (built at upload)
       const double *qa = g.qabs + ((size_t)(kr0 - 1) * nka + (ia - 1)) * nkt * MB;
+      double qv[MB];
+#pragma unroll
+      for (int ib = 1; ib <= MB; ++ib) qv[ib - 1] = qa[(ib - 1) * nkt + jt - 1];
       double rad = 0.0;
-      for (int ib = ib0; ib <= MB; ++ib)
-        rad = rad + s_totr[ib - 1] * (qa[(jt - 1) * MB + ib - 1] * de0 + qa[(jtp - 1) * MB + ib - 1] * dep) / de0p;
+#pragma unroll
+      for (int ib = 1; ib <= MB; ++ib)
+        if (ib >= ib0) rad = rad + s_totr[ib - 1] * qv[ib - 1] / de0p;
       s_sr[q] = srq;
       s_cd[q] = 3.e12 * rho21 * xkas / (x1 * rk * rk * rho21s * srq);
       s_cr[q] = rad * 7.5e5 / (rk * x1) - kRhow * 4190. * (tn - to0) / (dt * x1);
@@ -336,14 +395,52 @@ kon_subkon_kernel(KonGridDev g, long long ncell, double dt, KonArgs A)
     if (threadIdx.x == 0) { s_flag[0] = 0; s_flag[1] = 0; }
     cp_async_wait_all();
     __syncthreads();
+    KP(1);
     for (int itk = 1; itk <= 10; ++itk) {
+      for (int r0 = 0; r0 < nka; r0 += rch) {
+        const int nr = min(rch, nka - r0);
+        if (threadIdx.x < nr) { s_w[threadIdx.x] = 0; s_iend[threadIdx.x] = nkt + 1; }
+        __syncthreads();
+        // part A: one thread per (dry class, source bin)
+        for (int q = threadIdx.x; q < nr * nkt; q += blockDim.x) {
+          const int rr = q / nkt, i = q - rr * nkt + 1, r = (r0 + rr) * nkt;
+          RowCoef rc{s_cd + r, s_cr + r, s_sr + r, fquer, g.dlne, nkt};
+          double x1 = 0.0;
+          const unsigned cd = advec_flux(nkt, dt, rc, s_falt + r, i, &x1);
+          s_code[q] = (unsigned short)cd;
+          s_x1[q] = x1;
+          const unsigned kind = cd >> 8;
+          if (kind == ADV_ERR) { atomicMin(&s_iend[rr], i); s_flag[1] = 1; }
+          else if (kind != ADV_SKIP) {
+            const int d = abs((int)(cd & 255u) - i);
+            if (d > s_w[rr]) atomicMax(&s_w[rr], d);
+          }
+        }
+        __syncthreads();
+        KP(2);
+        // part B: one thread per (dry class, target bin), ordered additions
+        for (int q = threadIdx.x; q < nr * nkt; q += blockDim.x) {
+          const int rr = q / nkt, k = q - rr * nkt + 1, r = (r0 + rr) * nkt;
+          s_ffk[r + k - 1] = advec_gather(nkt, k, s_w[rr], s_iend[rr], s_falt + r, s_x1 + rr * nkt, s_code + rr * nkt);
+        }
+        if (r0 + rch < nka) __syncthreads();   // the flux buffer, s_w and s_iend are reused by the next chunk
+        KP(3);
+      }
+      __syncthreads();
+      // each class' water change (per row, in bin order; the differences and products do not
+      // depend on the running sum, so they are formed four bins ahead of it)
       if (threadIdx.x < nka) {
         const int r = threadIdx.x * nkt;
-        RowCoef rc{s_cd + r, s_cr + r, s_sr + r, fquer, g.dlne, nkt};
-        const int bad = advec_row(nkt, dt, rc, s_falt + r, s_ffk + r);
-        if (bad) s_flag[1] = 1;
         double dw = 0.0;
-        for (int jt = 0; jt < nkt; ++jt) dw = dw + (s_ffk[r + jt] - s_falt[r + jt]) * s_e[jt];
+        int jt = 0;
+        for (; jt + 4 <= nkt; jt += 4) {
+          const double p0 = (s_ffk[r + jt] - s_falt[r + jt]) * s_e[jt];
+          const double p1 = (s_ffk[r + jt + 1] - s_falt[r + jt + 1]) * s_e[jt + 1];
+          const double p2 = (s_ffk[r + jt + 2] - s_falt[r + jt + 2]) * s_e[jt + 2];
+          const double p3 = (s_ffk[r + jt + 3] - s_falt[r + jt + 3]) * s_e[jt + 3];
+          dw = dw + p0; dw = dw + p1; dw = dw + p2; dw = dw + p3;
+        }
+        for (; jt < nkt; ++jt) dw = dw + (s_ffk[r + jt] - s_falt[r + jt]) * s_e[jt];
         s_dw[threadIdx.x] = dw;
       }
       __syncthreads();
@@ -374,6 +471,7 @@ kon_subkon_kernel(KonGridDev g, long long ncell, double dt, KonArgs A)
         s_flag[0] = stop;
       }
       __syncthreads();
+      KP(4);
       fquer = s_it[0];
       if (s_flag[0]) break;
     }
@@ -430,6 +528,7 @@ kon_subkon_kernel(KonGridDev g, long long ncell, double dt, KonArgs A)
     } else {
       for (int i = threadIdx.x; i < ntile; i += blockDim.x) ffk[i] = s_ffk[i];
     }
+    KP(5);
   }
 }
 
@@ -464,7 +563,7 @@ int check_grid(const mistra_kon_grid *g)
 {
   if (!g || !g->en || !g->rn || !g->b0m || !g->ew || !g->e || !g->dew || !g->rw || !g->qabs)
     return mistra_internal_fail(MISTRA_KPP_EINVAL, "null grid");
-  if (g->nka < 1 || g->nka > KON_THREADS || g->nkt < 5 || g->nkt > MAXK)
+  if (g->nka < 1 || g->nka > KON_MAX_NKA || g->nkt < 5 || g->nkt > MAXK)
     return mistra_internal_fail(MISTRA_KPP_EINVAL, "grid size out of range (nka <= 128, 5 <= nkt <= 128)");
   if (!(g->dlne > 0.0)) return mistra_internal_fail(MISTRA_KPP_EINVAL, "dlne <= 0");
   return 0;
@@ -473,7 +572,16 @@ int check_grid(const mistra_kon_grid *g)
 size_t smem_bytes(const mistra_kon_grid *g)
 {
   const size_t ntile = (size_t)g->nka * g->nkt;
-  return sizeof(double) * (5 * ntile + g->nka + g->nkt + MB + 2) + sizeof(int) * (2 + g->nka + 2);
+  return sizeof(double) * (5 * ntile + g->nka + g->nkt + MB + 2) + sizeof(int) * ((g->nka + 5) & ~1);
+}
+
+// rows per part-A/B chunk: what the flux buffer (8 + 2 bytes per grid point) can hold
+int rows_per_chunk(const mistra_kon_grid *g)
+{
+  const size_t base = smem_bytes(g), cap = 227 * 1024;
+  if (base >= cap) return 0;
+  size_t r = (cap - base - 32) / ((size_t)g->nkt * 10 + 8);
+  return (int)(r > (size_t)g->nka ? (size_t)g->nka : r);
 }
 
 int grid_to_device(const mistra_kon_grid *g, cudaStream_t st, KonGridDev *out, GridCache **cache, bool full)
@@ -518,7 +626,26 @@ int grid_to_device(const mistra_kon_grid *g, cudaStream_t st, KonGridDev *out, G
     gc.kw.swap(kwv);
     gc.nka = g->nka;
     gc.nkt = g->nkt;
-    CKK(cudaMemcpyAsync(gc.d, gc.host.data(), sizeof(double) * gc.host.size(), cudaMemcpyHostToDevice, st));
+    {
+      // device copy of qabs: per band the bin-width-weighted pair of str.f90:5144-5145,
+      // qabs(ib,jt)*dew(jt) + qabs(ib,jtp)*dew(jtp) (a pure function of the grid, same
+      // arithmetic as the reference), laid out [kr][ia][ib][jt] so that a warp's loads of one
+      // band are contiguous
+      std::vector<double> up(gc.host);
+      const size_t q0 = 3 * nka + 3 * nkt + nka * nkt;
+      const double *dewh = gc.host.data() + 3 * nka + 2 * nkt;
+      for (size_t ra = 0; ra < (size_t)MISTRA_JPTAERRAD * nka; ++ra)
+        for (size_t jt = 0; jt < nkt; ++jt) {
+          const size_t jtp = jt + 1 < nkt ? jt + 1 : nkt - 1;
+          for (size_t ib = 0; ib < (size_t)MB; ++ib) {
+            const double qa = gc.host[q0 + (ra * nkt + jt) * MB + ib], qb = gc.host[q0 + (ra * nkt + jtp) * MB + ib];
+            const double t0 = qa * dewh[jt], t1 = qb * dewh[jtp];
+            up[q0 + (ra * MB + ib) * nkt + jt] = t0 + t1;
+          }
+        }
+      CKK(cudaMemcpyAsync(gc.d, up.data(), sizeof(double) * up.size(), cudaMemcpyHostToDevice, st));
+      CKK(cudaStreamSynchronize(st));
+    }
     CKK(cudaMemcpyAsync(gc.d_kw, gc.kw.data(), sizeof(int) * nka, cudaMemcpyHostToDevice, st));
     CKK(cudaStreamSynchronize(st));
     gc.valid = true;
@@ -541,8 +668,9 @@ int grid_to_device(const mistra_kon_grid *g, cudaStream_t st, KonGridDev *out, G
 
 int launch(const mistra_kon_grid *g, int64_t ncell, double dt, const KonArgs &A, void *stream)
 {
-  const size_t smem = smem_bytes(g);
-  if (smem > 227 * 1024) return mistra_internal_fail(MISTRA_KPP_EINVAL, "grid too large for shared memory");
+  const int rch = rows_per_chunk(g);
+  if (rch < 1) return mistra_internal_fail(MISTRA_KPP_EINVAL, "grid too large for shared memory");
+  const size_t smem = smem_bytes(g) + (((size_t)rch * ((size_t)g->nkt * 10 + 8) + 31) & ~(size_t)15);
   std::lock_guard<std::mutex> lk(g_mu);
   cudaStream_t st = (cudaStream_t)stream;
   KonGridDev gd;
@@ -553,7 +681,7 @@ int launch(const mistra_kon_grid *g, int64_t ncell, double dt, const KonArgs &A,
   if (per_sm < 1) per_sm = 1;
   long long blocks = (long long)gc->num_sm * per_sm;
   if (blocks > ncell) blocks = ncell;
-  kon_subkon_kernel<<<(int)blocks, KON_THREADS, smem, st>>>(gd, ncell, dt, A);
+  kon_subkon_kernel<<<(int)blocks, KON_THREADS, smem, st>>>(gd, ncell, dt, A, rch);
   CKK(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;
@@ -711,5 +839,16 @@ int mistra_kon_layers(const mistra_kon_grid *g, int64_t ncell, double dt, int ch
 }
 
 int64_t mistra_kon_launch_count(void) { return g_launches.load(); }
+
+#ifdef KON_PROF
+int mistra_kon_prof(unsigned long long *out)
+{
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_kon_prof, sizeof(unsigned long long) * 8);
+  unsigned long long z[8] = {0};
+  cudaMemcpyToSymbol(g_kon_prof, z, sizeof z);
+  return (int)e;
+}
+#endif
 
 }  // extern "C"

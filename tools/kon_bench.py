@@ -28,3 +28,12 @@ for i in range(it):
     ms = e[0].elapsed_time(e[1])
     print("iter %d: subkon %.3f ms for %d layers = %.0f layers/s; mean iterations %.2f" % (
         i, ms, n, n / (ms * 1e-3), st.float().mean().item()))
+if os.environ.get("MISTRA_KPP_LIB", "").endswith("_konprof.so"):
+    import ctypes as C
+    from mistra_b200 import kpp
+    buf = (C.c_ulonglong * 8)()
+    kpp.library().mistra_kon_prof(buf)
+    v = list(buf)[:6]
+    names = ["layer scalars + tile copy issue", "coefficient setup", "part A (flux)", "part B (ordered adds)", "secant update", "write back"]
+    for nm, c in zip(names, v):
+        print("%-34s %6.2f%%  %.0f cycles/layer" % (nm, 100.0 * c / sum(v), c / float(n * it)))
