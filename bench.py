@@ -357,25 +357,36 @@ def run_b200(args):
         hb = []
         for mname, var, rc, fix in batches:
             hv0 = torch.from_numpy(var).pin_memory()
+            nc = hv0.shape[0]
+            dgp = (torch.empty(nc, dtype=torch.int32).pin_memory(), torch.empty((nc, 8), dtype=torch.int32).pin_memory(),
+                   torch.empty(nc, dtype=torch.float64).pin_memory(), torch.empty(nc, dtype=torch.float64).pin_memory())
             hb.append((MECH_ID[mname], hv0, torch.empty_like(hv0).pin_memory(),
-                       torch.from_numpy(rc).pin_memory(), torch.from_numpy(fix).pin_memory()))
-        h2d = sum(v0.numel() * 8 + r.numel() * 8 + f.numel() * 8 for _, v0, _, r, f in hb)
-        d2h = sum(v0.numel() * 8 + v0.shape[0] * (4 + 32 + 8) for _, v0, _, r, f in hb)
+                       torch.from_numpy(rc).pin_memory(), torch.from_numpy(fix).pin_memory(), dgp))
+        h2d = sum(v0.numel() * 8 + r.numel() * 8 + f.numel() * 8 for _, v0, _, r, f, _ in hb)
+        d2h = sum(v0.numel() * 8 + v0.shape[0] * (4 + 32 + 8 + 8) for _, v0, _, r, f, _ in hb)
 
         def step_host():
+            # every buffer is pinned host memory; the saved state is restored outside the clock
+            # (it is the bench's bookkeeping, not part of the path), the call itself moves
+            # rconst, fix, var to the device and var, ierr, stats, hexit, texit back
+            for mech, v0, v, r, f, dg in hb:
+                v.copy_(v0)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
             acc = 0
-            for mech, v0, v, r, f in hb:
-                _, ierr, stats, hexit, _tx = kpp.integrate(mech, r.numpy(), f.numpy(), v0.numpy(), out=v.numpy())
+            for mech, v0, v, r, f, dg in hb:
+                vn = v.numpy()
+                _, ierr, stats, hexit, _tx = kpp.integrate(mech, r.numpy(), f.numpy(), vn, out=vn,
+                                                           diag=tuple(t.numpy() for t in dg))
                 acc += int((ierr != 1).sum())
-            return acc
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0
         for _ in range(max(1, args.warmup - 1)):
             step_host()
-        barrier()
-        t0 = time.perf_counter()
+        dt = 0.0
         for _ in range(args.steps):
-            step_host()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+            dt += step_host()
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)

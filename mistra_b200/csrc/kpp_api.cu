@@ -20,7 +20,8 @@ thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 
 struct MechState {
-  double *ws = nullptr;
+  double *ws = nullptr;    // lane workspace of kernels on the caller's stream
+  double *ws2 = nullptr;   // second workspace: odd chunks of the host-buffer pipeline (allocated on first use)
   size_t ws_bytes = 0;
   int blocks = 0;
   int coef_variant = -1;  // -1 unset, 0 f64 literals, 1 f32 literals
@@ -31,14 +32,14 @@ struct DeviceState {
   int dev = -1;
   int num_sm = 0;
   cudaStream_t stream = nullptr;
-  unsigned long long *counter = nullptr;
+  unsigned long long *counter = nullptr;   // [2]: one cell counter per pipeline slot
   MechState mech[3];
   // device staging for the host-buffer entry
   void *d_stage = nullptr;
   size_t d_stage_bytes = 0;
   // copy streams / events of the chunk pipeline of the host-buffer entry
-  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-  cudaEvent_t ev_h[64] = {}, ev_k[64] = {}, ev_start = nullptr;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_k2 = nullptr;
+  cudaEvent_t ev_h[64] = {}, ev_k[64] = {}, ev_start = nullptr, ev_join = nullptr;
 };
 
 constexpr int kMaxDev = 16;
@@ -93,7 +94,7 @@ int get_device(DeviceState **out)
     d.dev = dev;
     d.num_sm = p.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-    CK(cudaMalloc(&d.counter, sizeof(unsigned long long)));
+    CK(cudaMalloc(&d.counter, 2 * sizeof(unsigned long long)));
     d.init = true;
   }
   *out = &d;
@@ -175,7 +176,7 @@ int ensure_mech(DeviceState &d, int mech, const KppMechInfo *mi, int f32, cudaSt
 int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rconst,
                   const double *d_fix, double *d_var, double t0, double t1,
                   const mistra_kpp_opts *o, int32_t *d_ierr, int32_t *d_stats, double *d_hexit,
-                  double *d_texit, cudaStream_t st)
+                  double *d_texit, cudaStream_t st, int slot = 0)
 {
   const KppMechInfo *mi = mech_info(mech);
   KppBatch b;
@@ -194,9 +195,19 @@ int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rcons
   b.hexit = d_hexit;
   b.texit = d_texit;
   b.ncell = ncell;
-  b.ws = ms.ws;
-  b.counter = d.counter;
-  CK(cudaMemsetAsync(d.counter, 0, sizeof(unsigned long long), st));
+  // stagger = 1/8 of one Ros3 attempt of a resident warp (measured with the phase-timer build:
+  // 1.3e6 / 8.7e6 cycles for gas / aer; tot scaled by its LU size); only when the batch is
+  // several waves long, so that the start-up delay is noise.  MISTRA_KPP_STAGGER overrides.
+  {
+    static const long long kAttempt[3] = {1300000, 8700000, 24000000};
+    b.stagger = (ncell >= 2LL * ms.blocks * KPP_BLOCK) ? kAttempt[mech] / 8 : 0;
+    if (const char *e = getenv("MISTRA_KPP_STAGGER")) b.stagger = atoll(e);
+    b.num_sm = d.num_sm;
+  }
+  if (slot == 1 && !ms.ws2) CK(cudaMalloc(&ms.ws2, ms.ws_bytes));
+  b.ws = slot ? ms.ws2 : ms.ws;
+  b.counter = d.counter + slot;
+  CK(cudaMemsetAsync(b.counter, 0, sizeof(unsigned long long), st));
   long long need_blocks = (ncell + KPP_BLOCK - 1) / KPP_BLOCK;
   int blocks = (int)(need_blocks < ms.blocks ? need_blocks : ms.blocks);
   CK(mi->launch(b, blocks, st));
@@ -339,15 +350,17 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
   int32_t *d_st = (int32_t *)p;
 
   // Pipeline over chunks of cells: H2D of chunk c+1 and D2H of chunk c-1 overlap the
-  // kernel of chunk c (copy streams + events; kernels stay in order on `st`, so the
-  // lane workspace and the cell counter are never shared by two running kernels).
+  // kernel of chunk c (copy streams + events).  Kernels alternate between two slots - the
+  // caller's stream with the first lane workspace / cell counter, an internal stream with the
+  // second - so that the CTAs of chunk c+1 move in as those of chunk c run out of cells
+  // instead of waiting for its slowest cell (a drained grid per chunk cost ~25 % end to end).
   // Host buffers may be pageable (Fortran arrays) or pinned; cudaMemcpyAsync handles
   // both, only pinned ones actually overlap.
   if ((rc = ensure_mech(*d, mech, mi, o ? (o->f32_literals ? 1 : 0) : 1, st))) return rc;
   const int64_t resident = (int64_t)d->mech[mech].blocks * KPP_BLOCK;
-  int64_t nchunk = ncell / (4 * resident);
+  int64_t nchunk = ncell / (2 * resident);
   if (nchunk < 1) nchunk = 1;
-  if (nchunk > 8) nchunk = 8;
+  if (nchunk > 16) nchunk = 16;
   if (const char *e = getenv("MISTRA_KPP_CHUNKS")) {
     int v = atoi(e);
     if (v >= 1 && v <= 64) nchunk = v;
@@ -356,6 +369,8 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
   if (!d->s_h2d) {
     CK(cudaStreamCreateWithFlags(&d->s_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&d->s_d2h, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&d->s_k2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
     for (auto &e : d->ev_h) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : d->ev_k) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&d->ev_start, cudaEventDisableTiming));
@@ -364,7 +379,10 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
   CK(cudaEventRecord(d->ev_start, st));
   CK(cudaStreamWaitEvent(d->s_h2d, d->ev_start, 0));
   CK(cudaStreamWaitEvent(d->s_d2h, d->ev_start, 0));
+  CK(cudaStreamWaitEvent(d->s_k2, d->ev_start, 0));
   for (int64_t c = 0, off = 0; off < ncell; ++c, off += per) {
+    const int slot = (int)(c & 1);
+    cudaStream_t ks = slot ? d->s_k2 : st;
     const size_t m = (size_t)((ncell - off) < per ? (ncell - off) : per), o0 = (size_t)off;
     CK(cudaMemcpyAsync(d_rc + o0 * mi->nreact, rconst + o0 * mi->nreact, m * mi->nreact * 8,
                        cudaMemcpyHostToDevice, d->s_h2d));
@@ -373,13 +391,18 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
     CK(cudaMemcpyAsync(d_vr + o0 * mi->nvar, var + o0 * mi->nvar, m * mi->nvar * 8,
                        cudaMemcpyHostToDevice, d->s_h2d));
     CK(cudaEventRecord(d->ev_h[c], d->s_h2d));
-    CK(cudaStreamWaitEvent(st, d->ev_h[c], 0));
+    CK(cudaStreamWaitEvent(ks, d->ev_h[c], 0));
     rc = launch_device(*d, mech, (int64_t)m, d_rc + o0 * mi->nreact, d_fx + o0 * mi->nfix,
                        d_vr + o0 * mi->nvar, t0, t1, o, ierr ? d_ie + o0 : nullptr,
                        stats ? d_st + o0 * 8 : nullptr, hexit ? d_hx + o0 : nullptr,
-                       texit ? d_tx + o0 : nullptr, st);
+                       texit ? d_tx + o0 : nullptr, ks, slot);
     if (rc) return rc;
-    CK(cudaEventRecord(d->ev_k[c], st));
+    CK(cudaEventRecord(d->ev_k[c], ks));
+  }
+  // results: queued after every input copy and kernel, so that a blocking copy into pageable
+  // host memory (Fortran arrays) stalls this thread only, not the chunks behind it
+  for (int64_t c = 0, off = 0; off < ncell; ++c, off += per) {
+    const size_t m = (size_t)((ncell - off) < per ? (ncell - off) : per), o0 = (size_t)off;
     CK(cudaStreamWaitEvent(d->s_d2h, d->ev_k[c], 0));
     CK(cudaMemcpyAsync(var + o0 * mi->nvar, d_vr + o0 * mi->nvar, m * mi->nvar * 8,
                        cudaMemcpyDeviceToHost, d->s_d2h));
@@ -388,6 +411,8 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
     if (hexit) CK(cudaMemcpyAsync(hexit + o0, d_hx + o0, m * 8, cudaMemcpyDeviceToHost, d->s_d2h));
     if (texit) CK(cudaMemcpyAsync(texit + o0, d_tx + o0, m * 8, cudaMemcpyDeviceToHost, d->s_d2h));
   }
+  CK(cudaEventRecord(d->ev_join, d->s_k2));     // the caller's stream ends after both slots
+  CK(cudaStreamWaitEvent(st, d->ev_join, 0));
   CK(cudaStreamSynchronize(d->s_d2h));
   CK(cudaStreamSynchronize(st));
   return 0;
@@ -407,6 +432,7 @@ int mistra_kpp_finalize(void)
     cudaDeviceSynchronize();
     for (auto &m : d.mech) {
       if (m.ws) cudaFree(m.ws);
+      if (m.ws2) cudaFree(m.ws2);
       m = MechState();
     }
     if (d.counter) cudaFree(d.counter);
@@ -414,6 +440,8 @@ int mistra_kpp_finalize(void)
     if (d.s_h2d) {
       cudaStreamDestroy(d.s_h2d);
       cudaStreamDestroy(d.s_d2h);
+      cudaStreamDestroy(d.s_k2);
+      cudaEventDestroy(d.ev_join);
       for (auto &e : d.ev_h) cudaEventDestroy(e);
       for (auto &e : d.ev_k) cudaEventDestroy(e);
       cudaEventDestroy(d.ev_start);

@@ -92,24 +92,36 @@ def spc_name(mech, i, strict=False):
     return s.decode() if s else None
 
 
-def integrate(mech, rconst, fix, var, t0=0.0, t1=10.0, opts=None, strict=False, out=None):
+def integrate(mech, rconst, fix, var, t0=0.0, t1=10.0, opts=None, strict=False, out=None, diag=None):
     """INTEGRATE_x for a batch of cells held in HOST numpy arrays.
 
-    rconst [ncell,NREACT], fix [ncell,NFIX], var [ncell,NVAR] (not modified).
+    rconst [ncell,NREACT], fix [ncell,NFIX], var [ncell,NVAR] (not modified; with out=var the
+    call advances var in place, as the C entry does).  `diag` = optional caller-owned
+    (ierr, stats, hexit, texit) arrays, e.g. views of pinned memory so that the chunk pipeline
+    of the library overlaps its copies.
     Returns (var_out, ierr[ncell], stats[ncell,8], hexit[ncell], texit[ncell])."""
     L = library(strict)
     nvar, nfix, nreact, _ = query(mech, strict)
     var_in = np.ascontiguousarray(var, dtype=np.float64).reshape(-1, nvar)
     ncell = var_in.shape[0]
     var_out = out if out is not None else np.empty_like(var_in)
-    if var_out is not var_in:
+    if var_out.shape != var_in.shape or var_out.dtype != np.float64 or not var_out.flags.c_contiguous:
+        raise KppError("integrate: bad out array")
+    if var_out.ctypes.data != var_in.ctypes.data:
         np.copyto(var_out, var_in)
     rconst = np.ascontiguousarray(rconst, dtype=np.float64).reshape(ncell, nreact)
     fix = np.ascontiguousarray(fix, dtype=np.float64).reshape(ncell, nfix)
-    ierr = np.zeros(ncell, dtype=np.int32)
-    stats = np.zeros((ncell, 8), dtype=np.int32)
-    hexit = np.zeros(ncell, dtype=np.float64)
-    texit = np.zeros(ncell, dtype=np.float64)
+    if diag is not None:
+        ierr, stats, hexit, texit = diag
+        for a, shp, dt in ((ierr, (ncell,), np.int32), (stats, (ncell, 8), np.int32),
+                           (hexit, (ncell,), np.float64), (texit, (ncell,), np.float64)):
+            if a.shape != shp or a.dtype != dt or not a.flags.c_contiguous:
+                raise KppError("integrate: bad diag array (need contiguous %s %s)" % (np.dtype(dt).name, shp))
+    else:
+        ierr = np.zeros(ncell, dtype=np.int32)
+        stats = np.zeros((ncell, 8), dtype=np.int32)
+        hexit = np.zeros(ncell, dtype=np.float64)
+        texit = np.zeros(ncell, dtype=np.float64)
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
     o = opts if opts is not None else default_opts(strict)
     rc = L.mistra_kpp_integrate(mech, ncell, rconst.ctypes.data_as(dp), fix.ctypes.data_as(dp),
