@@ -414,9 +414,11 @@ def run_b200(args):
 
     bins_res = None
     kon_res = None
+    next_res = None
     if not args.no_bins:
         bins_res = run_bins_leg(args, dev, world, rank, barrier)
         kon_res = run_kon_leg(args, dev, world, rank, barrier)
+        next_res = run_next_rows_leg(args, dev, world, rank, barrier)
 
     if rank == 0:
         clocks = clk.summary()
@@ -436,7 +438,7 @@ def run_b200(args):
             "diagnostics": {"sum_nstp": float(diag[0]), "sum_nrej": float(diag[1]),
                             "failed_cells": float(diag[2]), "cells": float(diag[3]),
                             "mean_steps_per_cell": float(diag[0] / max(1.0, float(diag[3])))},
-            "bins": bins_res, "kon": kon_res,
+            "bins": bins_res, "kon": kon_res, "next_rows": next_res,
             "per_mechanism": {k: {"kernel_ms": float(np.mean(v)),
                                   "cells_per_s": [d["n"] for d in dbatches if d["name"] == k][0] / (np.mean(v) * 1e-3)}
                               for k, v in kernel_ms.items()},
@@ -582,7 +584,9 @@ def run_kon_leg(args, dev, world, rank, barrier):
            "roofline": {"bound": "fp64", "kernel": "kon_subkon_kernel", "achieved": flops / (ms * 1e-3) * 1e-12,
                         "peak": peak, "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) * 1e-12 / peak,
                         "kernel_ms": ms, "traffic": None,
-                        "note": "latency-bound in this mapping: one CTA (70 active threads) per SM; "
+                        "note": "one CTA (512 threads) per SM, five 70x70 tiles in shared memory; the FP64 pipe "
+                                "mostly executes IEEE divisions (30 per grid point in the set-up, ~10 per flux), "
+                                "which the flop count above books as 1 flop each; "
                                 "HBM side: 2*nka*nkt*8 = %d B per layer -> %.4f of the measured copy bandwidth"
                                 % (2 * nk * 8, n * 2 * nk * 8 / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"])}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -594,6 +598,117 @@ def run_kon_leg(args, dev, world, rank, barrier):
         dt = time.perf_counter() - t1
         res["cpu_baseline"] = {"value": m * reps / dt, "unit": "layers/s", "cores": os.cpu_count(), "kind": "port",
                                "sample": "%d x %d layers, OpenMP over layers, %.1f s" % (reps, m, dt)}
+    return res
+
+
+def run_next_rows_leg(args, dev, world, rank, barrier):
+    """Rows N1 and N3 of SURVEY 8f, each timed on its own: Update_RCONST_a on the device
+    (gas.f:275-666 / aer.f:304-1400) and konc (kpp.f90:3370-3585).  Reported beside the headline."""
+    import torch
+    from mistra_b200 import konc, rconst as rcm, synthetic
+    peaks, peak_src = measured_peaks()
+    stream = torch.cuda.current_stream()
+    res = {}
+
+    def timeit(fn, restore=None):
+        ev = []
+        for i in range(args.warmup + args.steps):
+            if restore:
+                restore()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); fn(); e1.record(stream)
+            if i >= args.warmup:
+                ev.append((e0, e1))
+        barrier()
+        return float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+    # ---- konc ----
+    n = args.bins_layers * 8                                     # 0.24 M layers: 3.5 GB of sums + species
+    d = konc.synthetic_sums(n, seed=20261018 + rank)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    sums = {k: t(v) for k, v in d["sums"].items()}
+    vol2, pntot, sl0, si0 = t(d["vol2"]), t(d["pntot"]), t(d["sl1"]), t(d["sion1"])
+    sl1, sion1 = sl0.clone(), si0.clone()
+    l0 = konc.launch_count()
+    ms = timeit(lambda: konc.konc_device(d["ka"], sums, vol2, pntot, sl1, sion1),
+                restore=lambda: (sl1.copy_(sl0), sion1.copy_(si0)))
+    by = n * (2 * 4 * (konc.J2 + konc.J6) + 6 * 70 + 8) * 8
+    res["konc"] = {"metric": "konc_layers_per_s", "value": n * world / (ms * 1e-3), "unit": "layers/s",
+                   "layers_per_gpu": n, "ms_per_step": ms, "gpu_launches": int(konc.launch_count() - l0),
+                   "roofline": {"bound": "hbm", "kernel": "konc_kernel", "achieved": by / (ms * 1e-3) * 1e-9,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"],
+                                "peak_source": peak_src, "traffic": None,
+                                "note": "algorithmic bytes per layer = (2*4*(j2+j6) + 6*nka + 8)*8 = %d B" % (by // n)}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import konc_oracle as kco
+        m = min(n, 20000)
+        sub = {k: v[:m] for k, v in d["sums"].items()}
+        reps, t1 = 0, time.perf_counter()
+        while time.perf_counter() - t1 < 3.0:
+            kco.konc(d["ka"], sub, d["vol2"][:m], d["pntot"][:m], d["sl1"][:m], d["sion1"][:m])
+            reps += 1
+        dt = time.perf_counter() - t1
+        res["konc"]["cpu_baseline"] = {"value": m * reps / dt, "unit": "layers/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": "%d x %d layers, OpenMP over layers, %.1f s" % (reps, m, dt)}
+    del sums, vol2, pntot, sl0, si0, sl1, sion1
+    # ---- cw_rc ----
+    from mistra_b200 import cwrc, kon
+    g = kon.kon_grid()
+    n = args.bins_layers
+    st = kon.synthetic_columns(g, n, seed=20261018 + rank, dry_fraction=0.3)
+    ffh = st["ff"] * 100.0
+    cloudh = np.ones((n, 4), dtype=np.int32)
+    gd = {"nka": g["nka"], "nkt": g["nkt"], "ka": g["ka"], "kw": t(np.asarray(g["kw"], dtype=np.int32)),
+          "e": t(g["e"]), "rq": t(g["rq"])}
+    ffd, feud, cloudd = t(ffh), t(st["feu"]), t(cloudh)
+    outs = [torch.empty((n, 4), dtype=torch.float64, device=dev) for _ in range(4)]
+    l0 = cwrc.launch_count()
+    ms = timeit(lambda: cwrc.cw_rc_device(gd, ffd, feud, cloudd, *outs))
+    by = n * (g["nka"] * g["nkt"] * 8 + 8 + 16 + 4 * 32)
+    res["cw_rc"] = {"metric": "cw_rc_layers_per_s", "value": n * world / (ms * 1e-3), "unit": "layers/s",
+                    "layers_per_gpu": n, "ms_per_step": ms, "gpu_launches": int(cwrc.launch_count() - l0),
+                    "roofline": {"bound": "hbm", "kernel": "cwrc_kernel", "achieved": by / (ms * 1e-3) * 1e-9,
+                                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"],
+                                 "peak_source": peak_src, "traffic": None,
+                                 "note": "algorithmic bytes per layer = nka*nkt*8 + 152 = %d B (%.1f GB of ff: larger than L2)"
+                                         % (by // n, n * g["nka"] * g["nkt"] * 8e-9)}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cwrc_oracle as cwo
+        m = min(n, 8000)
+        reps, t1 = 0, time.perf_counter()
+        while time.perf_counter() - t1 < 3.0:
+            cwo.cw_rc(g, ffh[:m], st["feu"][:m], cloudh[:m])
+            reps += 1
+        dt = time.perf_counter() - t1
+        res["cw_rc"]["cpu_baseline"] = {"value": m * reps / dt, "unit": "layers/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": "%d x %d layers, OpenMP over layers, %.1f s" % (reps, m, dt)}
+    del ffd, feud, cloudd, outs
+    # ---- Update_RCONST_a ----
+    ens = synthetic.AerEnsemble(max(1, args.cols // 10), seed=20261018 + rank)
+    tn = lambda a: None if a is None else t(a)
+    fields = ("yhenry", "yxkmt", "ykef", "ykeb", "yxkmtd", "yxeq", "ycw", "ycwd")
+    kw = {k: tn(getattr(ens, k, None)) for k in fields}
+    cb1, scal, ph, conc = t(ens.cb1), t(ens.scal), t(ens.ph_rat), t(ens.conc())
+    out = torch.empty((ens.ncell, 979), dtype=torch.float64, device=dev)
+    ms = timeit(lambda: rcm.update_rconst_device(1, cb1, scal, ph, conc, out=out, **kw))
+    inb = sum(v.numel() for v in [cb1, scal, ph, conc] + [x for x in kw.values() if x is not None]) * 8
+    by = inb + out.numel() * 8
+    res["rconst"] = {"metric": "update_rconst_cells_per_s", "value": ens.ncell * world / (ms * 1e-3), "unit": "cells/s",
+                     "mechanism": "aer", "cells_per_gpu": ens.ncell, "ms_per_step": ms,
+                     "roofline": {"bound": "hbm", "kernel": "rconst_kernel<1>", "achieved": by / (ms * 1e-3) * 1e-9,
+                                  "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"],
+                                  "peak_source": peak_src, "traffic": None,
+                                  "note": "algorithmic bytes per cell = inputs as the host passes them (%d B, mostly the "
+                                          "NSPEC-indexed exchange arrays) + NREACT*8 out" % (inb // ens.ncell)}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        m = min(ens.ncell, 20000)
+        reps, t1 = 0, time.perf_counter()
+        while time.perf_counter() - t1 < 3.0:
+            ens.rconst(sl=slice(0, m))
+            reps += 1
+        dt = time.perf_counter() - t1
+        res["rconst"]["cpu_baseline"] = {"value": m * reps / dt, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
+                                         "sample": "%d x %d cells, host producer libmistra_rconst.so (OpenMP), %.1f s" % (reps, m, dt)}
     return res
 
 

@@ -138,3 +138,26 @@ module mistra_kon_mod
      end function mistra_kon_subkon
   end interface
 end module mistra_kon_mod
+
+! mistra_konc_mod - ISO_C_BINDING interface of include/mistra_konc.h: SUBROUTINE konc
+! (kpp.f90:3370-3585) for all layers 2..nf at once, on the COMMON arrays of /blck07/, /blck08/
+! and /blck17/ in place.
+module mistra_konc_mod
+  use, intrinsic :: iso_c_binding
+  implicit none
+  ! c_loc pointers to the first layer of the batch: vol1_a(nka,k) ... pntot(nkc,k), sl1(j2,nkc,k),
+  ! sion1(j6,nkc,k); warn(3,ncell) int32 or c_null_ptr
+  type, bind(C) :: mistra_konc_args
+     integer(c_int32_t) :: nka, ka, j2, j6
+     type(c_ptr) :: vol1_a, vol1_d, part_o_a, part_o_d, part_n_a, part_n_d, vol2, pntot, sl1, sion1, warn
+  end type mistra_konc_args
+  interface
+     function mistra_konc(ncell, a, stream) result(rc) bind(C, name="mistra_konc")
+       import :: c_int, c_int64_t, c_ptr, mistra_konc_args
+       integer(c_int64_t), value :: ncell
+       type(mistra_konc_args), intent(in) :: a
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_konc
+  end interface
+end module mistra_konc_mod

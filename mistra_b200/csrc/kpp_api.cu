@@ -40,6 +40,9 @@ struct DeviceState {
   // copy streams / events of the chunk pipeline of the host-buffer entry
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_k2 = nullptr;
   cudaEvent_t ev_h[64] = {}, ev_k[64] = {}, ev_start = nullptr, ev_join = nullptr;
+  // last kernel of each slot: a launch on another stream waits for it (the slot's workspace and
+  // cell counter must not be shared by two running kernels)
+  cudaEvent_t ev_slot[2] = {};
 };
 
 constexpr int kMaxDev = 16;
@@ -95,6 +98,7 @@ int get_device(DeviceState **out)
     d.num_sm = p.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&d.counter, 2 * sizeof(unsigned long long)));
+    for (auto &e : d.ev_slot) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     d.init = true;
   }
   *out = &d;
@@ -195,23 +199,29 @@ int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rcons
   b.hexit = d_hexit;
   b.texit = d_texit;
   b.ncell = ncell;
-  // stagger = 1/8 of one Ros3 attempt of a resident warp (measured with the phase-timer build:
-  // 1.3e6 / 8.7e6 cycles for gas / aer; tot scaled by its LU size); only when the batch is
-  // several waves long, so that the start-up delay is noise.  MISTRA_KPP_STAGGER overrides.
-  {
-    static const long long kAttempt[3] = {1300000, 8700000, 24000000};
-    b.stagger = (ncell >= 2LL * ms.blocks * KPP_BLOCK) ? kAttempt[mech] / 8 : 0;
-    if (const char *e = getenv("MISTRA_KPP_STAGGER")) b.stagger = atoll(e);
-    b.num_sm = d.num_sm;
-  }
   if (slot == 1 && !ms.ws2) CK(cudaMalloc(&ms.ws2, ms.ws_bytes));
   b.ws = slot ? ms.ws2 : ms.ws;
   b.counter = d.counter + slot;
+  CK(cudaStreamWaitEvent(st, d.ev_slot[slot], 0));
   CK(cudaMemsetAsync(b.counter, 0, sizeof(unsigned long long), st));
   long long need_blocks = (ncell + KPP_BLOCK - 1) / KPP_BLOCK;
   int blocks = (int)(need_blocks < ms.blocks ? need_blocks : ms.blocks);
   CK(mi->launch(b, blocks, st));
+  CK(cudaEventRecord(d.ev_slot[slot], st));
   g_launches.fetch_add(1);
+  return 0;
+}
+
+int ensure_streams(DeviceState *d)
+{
+  if (d->s_h2d) return 0;
+  CK(cudaStreamCreateWithFlags(&d->s_h2d, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&d->s_d2h, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&d->s_k2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
+  for (auto &e : d->ev_h) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : d->ev_k) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&d->ev_start, cudaEventDisableTiming));
   return 0;
 }
 
@@ -302,6 +312,24 @@ int mistra_kpp_integrate_device(int mech, int64_t ncell, const double *d_rconst,
   int rc = get_device(&d);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream, as in the CUDA runtime
+  // Experiment (MISTRA_KPP_SPLIT=1): the two halves of a long batch as two co-resident kernels.
+  static const bool split = getenv("MISTRA_KPP_SPLIT") && atoi(getenv("MISTRA_KPP_SPLIT")) > 0;
+  if (split && ncell >= 8LL * d->num_sm * 2 * KPP_BLOCK) {
+    const KppMechInfo *mi = mech_info(mech);
+    if ((rc = ensure_streams(d))) return rc;
+    const int64_t h = ncell / 2;
+    CK(cudaEventRecord(d->ev_start, st));
+    CK(cudaStreamWaitEvent(d->s_k2, d->ev_start, 0));
+    if ((rc = launch_device(*d, mech, h, d_rconst, d_fix, d_var, t0, t1, o, d_ierr, d_stats, d_hexit, d_texit, st, 0)))
+      return rc;
+    if ((rc = launch_device(*d, mech, ncell - h, d_rconst + h * mi->nreact, d_fix + h * mi->nfix, d_var + h * mi->nvar,
+                            t0, t1, o, d_ierr ? d_ierr + h : nullptr, d_stats ? d_stats + 8 * h : nullptr,
+                            d_hexit ? d_hexit + h : nullptr, d_texit ? d_texit + h : nullptr, d->s_k2, 1)))
+      return rc;
+    CK(cudaEventRecord(d->ev_join, d->s_k2));
+    CK(cudaStreamWaitEvent(st, d->ev_join, 0));
+    return 0;
+  }
   return launch_device(*d, mech, ncell, d_rconst, d_fix, d_var, t0, t1, o, d_ierr, d_stats,
                        d_hexit, d_texit, st);
 }
@@ -366,15 +394,7 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
     if (v >= 1 && v <= 64) nchunk = v;
   }
   const int64_t per = (ncell + nchunk - 1) / nchunk;
-  if (!d->s_h2d) {
-    CK(cudaStreamCreateWithFlags(&d->s_h2d, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&d->s_d2h, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&d->s_k2, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
-    for (auto &e : d->ev_h) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto &e : d->ev_k) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&d->ev_start, cudaEventDisableTiming));
-  }
+  if ((rc = ensure_streams(d))) return rc;
   // the copy streams must not run ahead of work already queued on the caller's stream
   CK(cudaEventRecord(d->ev_start, st));
   CK(cudaStreamWaitEvent(d->s_h2d, d->ev_start, 0));
@@ -436,6 +456,7 @@ int mistra_kpp_finalize(void)
       m = MechState();
     }
     if (d.counter) cudaFree(d.counter);
+    for (auto &e : d.ev_slot) if (e) cudaEventDestroy(e);
     if (d.d_stage) cudaFree(d.d_stage);
     if (d.s_h2d) {
       cudaStreamDestroy(d.s_h2d);

@@ -26,10 +26,6 @@ struct KppBatch {
   // decoded options (Rosenbrock_x, gas.f:950-1051)
   double t0, t1, rtol, atol, hmin, hmax, hstart, facmin, facmax, facrej, facsafe;
   int max_steps, autonomous;
-  // start-up stagger (SM cycles per resident-warp index, 0 = none): the warps of an SM start
-  // 1/8 of an attempt apart so that their memory-streaming and compute phases interleave
-  long long stagger;
-  int num_sm;
 };
 
 struct KppMechInfo {

@@ -23,6 +23,8 @@ def declared_functions(header):
                                         ("mistra_kpp.h", "libmistra_kpp_strict.so"),
                                         ("mistra_bins.h", "libmistra_kpp.so"),
                                         ("mistra_kon.h", "libmistra_kpp.so"),
+                                        ("mistra_konc.h", "libmistra_kpp.so"),
+                                        ("mistra_cwrc.h", "libmistra_kpp.so"),
                                         ("mistra_rconst_cuda.h", "libmistra_kpp.so"),
                                         ("mistra_rconst.h", "libmistra_rconst.so")])
 def test_library_exports_every_declared_symbol(kpp, header, lib):
