@@ -330,7 +330,7 @@ def run_b200(args):
     step_bytes = 8.0 * (8 * mdom.lu_nonzero + 40 * mdom.nvar + 4 * mdom.nreact)
     nstp_dom = float(dd["stats"][:, 2].sum().item())
     # measured DRAM traffic per Ros3 step from the committed ncu --set full captures (profiles/)
-    ncu_step_bytes = {"gas": 94.1e3, "aer": 626.0e3}.get(dom)
+    ncu_step_bytes = {"gas": 94.1e3, "aer": 565.6e3}.get(dom)   # profiles/r01_gas_*_ncu_full.txt, r01b_aer_ncu_full.txt
     roof = {
         "bound": "hbm", "kernel": "ros3_kernel_%s" % mdom.suffix,
         "achieved": step_bytes * nstp_dom / (kms * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -14,9 +14,10 @@
  *   rc, cw, cm, conv2 [ncell][4]   COMMON /blck11/, /blck12/, /blck13/   out
  *   kw [nka] (1-based limit), e [nkt], rq [nka][nkt]   COMMON /blck06/, /cb50/
  * Numerics: binary64, the reference's expressions without FMA contraction; the twelve sums are
- * formed per dry class first and then over the classes of the bin (the reference keeps one
- * running sum over all (ia, jt) of a bin, a chain of up to 2660 additions): all terms are
- * non-negative, results agree with the reference order to ~1e-14 relative (tests: 1e-13).
+ * formed as 256 interleaved partial sums (dry classes ia = w mod 8, water bins jt = l mod 32 per
+ * warp w and lane l) combined by a fixed butterfly over the lanes and then over the warps in order
+ * (the reference keeps one running sum over all (ia, jt) of a bin, a chain of up to 2660 additions): all terms are non-negative, results agree
+ * with the reference order to ~1e-14 relative (tests: 1e-13).
  * Returns 0 or MISTRA_KPP_E* (mistra_kpp.h).  No CPU fallback. */
 #ifndef MISTRA_CWRC_H
 #define MISTRA_CWRC_H

@@ -1,12 +1,14 @@
 // SUBROUTINE cw_rc on the device (include/mistra_cwrc.h): CUDA kernel + C-ABI entries.
 // Role in the reference: the layer loop of /root/reference/src/kpp.f90:2260-2412.
 //
-// Mapping: one CTA (256 threads) per layer.  The 70 x 70 spectrum is staged in shared memory
-// with coalesced loads (rows padded to an odd stride), two threads per dry class then sum the
-// class' aerosol part (jt <= kw) and droplet part in bin order - three sums each: volume cw,
-// volume x radius rc, water mass cm (kpp.f90:2285-2322) - and four threads add the classes of
-// their chemistry bin in class order and apply the switches (2335-2410).  HBM-bound: nka*nkt*8 =
-// 39.2 kB read per layer, 128 B written.  No FMA contraction (build.py).
+// Mapping: one CTA (256 threads) per layer; the layer's 70 x 70 spectrum goes to shared memory with
+// 16-byte asynchronous copies (the whole tile in flight at once), then one warp per dry class at a
+// time: the lanes stride over the class' water bins (rq and e come from the L1/L2-resident grid
+// tables) and keep, over all classes of their warp, the sums volume cw, volume x radius rc and water
+// mass cm (kpp.f90:2285-2322) of the four chemistry bins (aerosol part jt <= kw / droplet part, small
+// classes ia <= ka / large ones); one fixed butterfly per sum adds the lanes, twelve threads add the
+// warps in order and four apply the switches (2335-2410).  HBM-bound: nka*nkt*8 = 39.2 kB read per
+// layer, 128 B written.  No FMA contraction (build.py).
 #include "../../include/mistra_cwrc.h"
 #include "../../include/mistra_kpp.h"
 
@@ -24,44 +26,78 @@ namespace {
 constexpr int CWRC_THREADS = 256;
 constexpr int CWRC_MAX = 128;   // nka, nkt
 
+__device__ __forceinline__ double warp_sum(double v)
+{
+  // fixed butterfly: the same tree for every class and layer, so the result is deterministic
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
 __global__ void __launch_bounds__(CWRC_THREADS) cwrc_kernel(long long ncell, mistra_cwrc_args a)
 {
-  extern __shared__ double sm[];
-  const int nka = a.nka, nkt = a.nkt, ld = nkt | 1;
-  double *s_ff = sm;                     // [nka][ld]
-  double *s_p = s_ff + nka * ld;         // [2*nka][3] partial sums of (class, part)
+  __shared__ double s_p[(CWRC_THREADS / 32) * 12];   // per warp: [bin][cw, rc, cm]
+  __shared__ double s_b[12];                 // sums of the chemistry bins
+  const int nka = a.nka, nkt = a.nkt;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const double xpi = 4.0 / 3.0 * 3.1415926535897932;   // kpp.f90:2204, constants.f90 pi
+  extern __shared__ __align__(16) double s_ff[];       // [nka][nkt] the layer's spectrum
+  const int ntile = nka * nkt;
   for (long long c = blockIdx.x; c < ncell; c += gridDim.x) {
     __syncthreads();
-    const double *f = a.ff + (size_t)c * nka * nkt;
-    for (int q = threadIdx.x; q < nka * nkt; q += blockDim.x) {
-      const int ia = q / nkt, jt = q - ia * nkt;
-      s_ff[ia * ld + jt] = f[q];
+    // the whole tile in flight at once (16-byte asynchronous copies, no register staging)
+    const double *gf = a.ff + (size_t)c * ntile;
+    if ((ntile & 1) == 0) {
+      for (int q = threadIdx.x; q < (ntile >> 1); q += blockDim.x)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(s_ff + 2 * q)),
+                     "l"(gf + 2 * q) : "memory");
+    } else {
+      for (int q = threadIdx.x; q < ntile; q += blockDim.x)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(s_ff + q)),
+                     "l"(gf + q) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+    const double *f = s_ff;
+    // one warp per dry class at a time: lanes stride over the water bins (coalesced loads of ff and
+    // rq); each lane keeps, over all classes of its warp, the sums of the four chemistry bins
+    double acc[12];                          // [bin][cw, rc, cm], compile-time indices only
+#pragma unroll
+    for (int q = 0; q < 12; ++q) acc[q] = 0.0;
+    for (int ia = warp + a.ial - 1; ia < nka; ia += nwarp) {
+      const int kwa = a.kw[ia];
+      const bool small = ia < a.ka;          // warp-uniform: bins 1|3, else 2|4
+      for (int jt = lane; jt < nkt; jt += 32) {
+        const double ffv = f[ia * nkt + jt], r = a.rq[ia * nkt + jt];
+        const double x0 = ffv * xpi * (r * r * r);
+        const double x1 = x0 * r, x2 = ffv * a.e[jt];
+        const bool aer = jt < kwa;
+        if (small) {
+          if (aer) { acc[0] = acc[0] + x0; acc[1] = acc[1] + x1; acc[2] = acc[2] + x2; }
+          else     { acc[6] = acc[6] + x0; acc[7] = acc[7] + x1; acc[8] = acc[8] + x2; }
+        } else {
+          if (aer) { acc[3] = acc[3] + x0; acc[4] = acc[4] + x1; acc[5] = acc[5] + x2; }
+          else     { acc[9] = acc[9] + x0; acc[10] = acc[10] + x1; acc[11] = acc[11] + x2; }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 12; ++q) acc[q] = warp_sum(acc[q]);
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < 12; ++q) s_p[warp * 12 + q] = acc[q];
     }
     __syncthreads();
-    if (threadIdx.x < 2 * nka) {
-      const int ia = threadIdx.x >> 1, part = threadIdx.x & 1, kwa = a.kw[ia];
-      const int j0 = part ? kwa : 0, j1 = part ? nkt : kwa;
-      double cw = 0.0, rc = 0.0, cm = 0.0;
-      for (int jt = j0; jt < j1; ++jt) {
-        const double ffv = s_ff[ia * ld + jt], r = a.rq[ia * nkt + jt];
-        const double x0 = ffv * xpi * (r * r * r);
-        cw = cw + x0;
-        rc = rc + x0 * r;
-        cm = cm + ffv * a.e[jt];
-      }
-      double *o = s_p + threadIdx.x * 3;
-      o[0] = cw; o[1] = rc; o[2] = cm;
+    // twelve threads: (bin, quantity) over the warps, in warp order
+    if (threadIdx.x < 12) {
+      double t = 0.0;
+      for (int w = 0; w < nwarp; ++w) t = t + s_p[w * 12 + threadIdx.x];
+      s_b[threadIdx.x] = t;
     }
     __syncthreads();
     if (threadIdx.x < 4) {
-      const int kc = threadIdx.x, part = kc >> 1;
-      const int lo = (kc & 1) ? a.ka : a.ial - 1, hi = (kc & 1) ? nka : a.ka;
-      double cw = 0.0, rc = 0.0, cm = 0.0;
-      for (int ia = lo; ia < hi; ++ia) {
-        const double *p = s_p + (2 * ia + part) * 3;
-        cw = cw + p[0]; rc = rc + p[1]; cm = cm + p[2];
-      }
+      const int kc = threadIdx.x;
+      const double cw = s_b[kc * 3], rc = s_b[kc * 3 + 1], cm = s_b[kc * 3 + 2];
       const double feu = a.feu[c];
       a.rc[c * 4 + kc] = (cw > 0.0) ? rc / cw * 1.e-6 : 0.0;
       a.cw[c * 4 + kc] = cw * 1.e-12;
@@ -121,12 +157,12 @@ int mistra_cwrc_device(int64_t ncell, const mistra_cwrc_args *d_a, void *stream)
   CKW(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 16) return mistra_internal_fail(MISTRA_KPP_ENODEVICE, "device index out of range");
   CKW(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const size_t smem = sizeof(double) * ((size_t)d_a->nka * (d_a->nkt | 1) + 6 * (size_t)d_a->nka);
+  const size_t smem = sizeof(double) * (size_t)d_a->nka * d_a->nkt;
   if (!g_attr[dev]) {
-    CKW(cudaFuncSetAttribute(cwrc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CKW(cudaFuncSetAttribute(cwrc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024));
     g_attr[dev] = true;
   }
-  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  int per_sm = (int)((224 * 1024) / (smem + 2048));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 8) per_sm = 8;
   long long blocks = (long long)sms * per_sm;
