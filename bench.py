@@ -605,7 +605,7 @@ def run_next_rows_leg(args, dev, world, rank, barrier):
     """Rows N1 and N3 of SURVEY 8f, each timed on its own: Update_RCONST_a on the device
     (gas.f:275-666 / aer.f:304-1400) and konc (kpp.f90:3370-3585).  Reported beside the headline."""
     import torch
-    from mistra_b200 import konc, rconst as rcm, synthetic
+    from mistra_b200 import konc, kpp, rconst as rcm, synthetic
     peaks, peak_src = measured_peaks()
     stream = torch.cuda.current_stream()
     res = {}
@@ -682,7 +682,70 @@ def run_next_rows_leg(args, dev, world, rank, barrier):
         dt = time.perf_counter() - t1
         res["cw_rc"]["cpu_baseline"] = {"value": m * reps / dt, "unit": "layers/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": "%d x %d layers, OpenMP over layers, %.1f s" % (reps, m, dt)}
-    del ffd, feud, cloudd, outs
+    # ---- fast_k_mt_a (same ff; cw and cm as cw_rc just wrote them) ----
+    from mistra_b200 import fastkmt
+    rr = np.random.default_rng(20261018 + rank)
+    ns, nx = 262, 50
+    lexd = t(fastkmt.lex("aer"))
+    tt, pp = t(st["t"]), t(st["p"])
+    freepd = t(2.28e-5 * st["t"] / st["p"])
+    alphad = t(10.0 ** rr.uniform(-4, 0, (n, ns)))
+    vmeand = t(rr.uniform(100.0, 700.0, (n, ns)))
+    xkd = torch.zeros((n, 4, ns), dtype=torch.float64, device=dev)
+    vtd = torch.zeros((n, 4), dtype=torch.float64, device=dev)
+    fk = {}
+    for tag, ffx in (("synthetic", ffd), ("dense", None)):
+        if ffx is None:                                          # every grid point populated: the FP64-bound case
+            ffx = ffd + 1.0e-3
+            cwrc.cw_rc_device(gd, ffx, feud, cloudd, *outs)
+        l0 = fastkmt.launch_count()
+        ms = timeit(lambda: fastkmt.fast_k_mt_device(gd, lexd, ffx, freepd, tt, pp, outs[1], outs[2], alphad, vmeand,
+                                                      xkd, vtd))
+        torch.cuda.synchronize()
+        on = (outs[2] > 0).cpu().numpy()                         # bins with chemistry
+        kcg = np.where(np.arange(g["nkt"])[None, :] < np.asarray(g["kw"])[:, None], 0, 2) + \
+            np.where(np.arange(g["nka"])[:, None] < g["ka"], 0, 1)
+        pop = (ffx > 0).cpu().numpy()
+        npt = sum(int((pop[on[:, kc]] & (kcg == kc)[None]).sum()) for kc in range(4))   # points that enter the sums
+        flops = npt * nx * 7.0 + n * g["nka"] * g["nkt"] * 1.0   # per term: add, div, 4 mul, add (div = 1 flop); q = rqm/freep
+        by = n * (g["nka"] * g["nkt"] * 8 + 2 * ns * 8 + 11 * 8) + int(on.sum()) * nx * 8
+        fk[tag] = {"value": n * world / (ms * 1e-3), "ms_per_step": ms, "gpu_launches": int(fastkmt.launch_count() - l0),
+                   "populated_points_per_layer": npt / n, "bins_with_chemistry_per_layer": float(on.sum()) / n,
+                   "fp64": {"achieved": flops / (ms * 1e-3) * 1e-12, "unit": "TFLOP/s",
+                            "divisions_per_s": npt * nx / (ms * 1e-3)},
+                   "hbm": {"achieved": by / (ms * 1e-3) * 1e-9, "unit": "GB/s",
+                           "frac": by / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"]}}
+    p64 = kpp.fp64_peak_tflops()
+    for v in fk.values():
+        v["fp64"]["peak"] = p64
+        v["fp64"]["frac"] = v["fp64"]["achieved"] / p64
+    res["fast_k_mt"] = {"metric": "fast_k_mt_layers_per_s", "value": fk["synthetic"]["value"], "unit": "layers/s",
+                        "layers_per_gpu": n, "ms_per_step": fk["synthetic"]["ms_per_step"],
+                        "gpu_launches": fk["synthetic"]["gpu_launches"], "mechanism": "aer",
+                        "roofline": {"bound": "hbm", "kernel": "fastkmt_kernel", "achieved": fk["synthetic"]["hbm"]["achieved"],
+                                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": fk["synthetic"]["hbm"]["frac"],
+                                     "peak_source": peak_src, "traffic": None,
+                                     "note": "synthetic spectra populate ~4 % of the grid, so the layer is read faster than "
+                                             "it is integrated: HBM-side bytes per layer = nka*nkt*8 + 2*NSPEC*8 + 88 + 400 per "
+                                             "bin with chemistry; 'dense' = every grid point populated, FP64-bound: (nx + 1) "
+                                             "IEEE divisions per point, booked as 1 flop each"},
+                        "cases": fk}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import fastkmt_oracle as fko
+        m = min(n, 2000)
+        h = lambda x: x[:m].cpu().numpy()
+        cwrc.cw_rc_device(gd, ffd, feud, cloudd, *outs)
+        torch.cuda.synchronize()
+        reps, t1 = 0, time.perf_counter()
+        while time.perf_counter() - t1 < 3.0:
+            fko.fast_k_mt(g, fastkmt.lex("aer"), ffh[:m], h(freepd), h(tt), h(pp), h(outs[1]), h(outs[2]), h(alphad),
+                          h(vmeand), h(xkd), h(vtd))
+            reps += 1
+        dt = time.perf_counter() - t1
+        res["fast_k_mt"]["cpu_baseline"] = {"value": m * reps / dt, "unit": "layers/s", "cores": os.cpu_count(),
+                                            "kind": "port", "sample": "%d x %d layers (synthetic spectra; the reference "
+                                            "loop visits every grid point), OpenMP over layers, %.1f s" % (reps, m, dt)}
+    del ffd, feud, cloudd, outs, alphad, vmeand, xkd, vtd
     # ---- Update_RCONST_a ----
     ens = synthetic.AerEnsemble(max(1, args.cols // 10), seed=20261018 + rank)
     tn = lambda a: None if a is None else t(a)

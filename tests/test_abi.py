@@ -25,6 +25,7 @@ def declared_functions(header):
                                         ("mistra_kon.h", "libmistra_kpp.so"),
                                         ("mistra_konc.h", "libmistra_kpp.so"),
                                         ("mistra_cwrc.h", "libmistra_kpp.so"),
+                                        ("mistra_fastkmt.h", "libmistra_kpp.so"),
                                         ("mistra_rconst_cuda.h", "libmistra_kpp.so"),
                                         ("mistra_rconst.h", "libmistra_rconst.so")])
 def test_library_exports_every_declared_symbol(kpp, header, lib):
