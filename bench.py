@@ -746,6 +746,72 @@ def run_next_rows_leg(args, dev, world, rank, barrier):
                                             "kind": "port", "sample": "%d x %d layers (synthetic spectra; the reference "
                                             "loop visits every grid point), OpenMP over layers, %.1f s" % (reps, m, dt)}
     del ffd, feud, cloudd, outs, alphad, vmeand, xkd, vtd
+    # ---- difc (row N4, first piece): implicit vertical exchange of every chemical species ----
+    from mistra_b200 import difc as dm
+    ncol, nlev = max(1, args.cols // 5), 150
+    dc = dm.synthetic_columns(ncol, nlev, seed=20261018 + rank)
+    rows = ((93, 93), (24, 24), (121 * 4, 121 * 4), (55 * 4, 55 * 4))    # s1, s3, sl1, sion1 of the reference
+    rr = np.random.default_rng(20261018 + rank)
+    fd = [(torch.from_numpy(rr.uniform(0.5, 1.5, (ncol, nlev, r))).to(dev) * t(dc["am3"])[:, :, None], p) for r, p in rows]
+    dd = {k: t(dc[k]) for k in ("atkh", "w", "am3", "detw", "deta")}
+    l0 = dm.launch_count()
+    ms = timeit(lambda: dm.difc_device(60.0, dd["atkh"], dd["w"], dd["am3"], dd["detw"], dd["deta"], fd))
+    nsp = sum(p for _, p in rows)
+    by = ncol * nsp * (2 * (nlev - 2) + 1) * 8 + ncol * nlev * 3 * 8
+    res["difc"] = {"metric": "difc_columns_per_s", "value": ncol * world / (ms * 1e-3), "unit": "columns/s",
+                   "columns_per_gpu": ncol, "levels": nlev, "species_per_column": nsp, "ms_per_step": ms,
+                   "gpu_launches": int(dm.launch_count() - l0),
+                   "tridiagonal_systems_per_s": ncol * nsp * world / (ms * 1e-3),
+                   "roofline": {"bound": "hbm", "kernel": "difc_solve_kernel", "achieved": by / (ms * 1e-3) * 1e-9,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"],
+                                "peak_source": peak_src, "traffic": None,
+                                "note": "algorithmic bytes per species and column = (2*(n-2) + 1)*8 (every level read "
+                                        "once and written once) + 3*n*8 per column; %.1f GB of species arrays: larger "
+                                        "than L2; the four solve launches and the coefficient launch are timed together"
+                                        % (ncol * nsp * nlev * 8e-9)}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import difc_oracle as dfo
+        m = min(ncol, 200)
+        fh = [(a[:m].cpu().numpy(), p) for a, p in fd]
+        reps, t1 = 0, time.perf_counter()
+        while time.perf_counter() - t1 < 3.0:
+            dfo.difc(60.0, dc["atkh"][:m], dc["w"][:m], dc["am3"][:m], dc["detw"], dc["deta"], fh)
+            reps += 1
+        dt = time.perf_counter() - t1
+        res["difc"]["cpu_baseline"] = {"value": m * reps / dt, "unit": "columns/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": "%d x %d columns, OpenMP over columns (includes a copy of the arrays), "
+                                                 "%.1f s" % (reps, m, dt)}
+    del fd
+    # ---- difp: the same exchange for the 70 x 70 particle spectrum of every level ----
+    ncp = max(1, ncol // 4)                                        # 500 columns: 2.9 GB of ff
+    rho = t(1.2 * np.exp(-np.cumsum(dc["detw"])[None] / 8000.0) * np.ones((ncp, 1)))
+    ffp = torch.rand((ncp, nlev, 4900), dtype=torch.float64, device=dev)
+    fsp = torch.zeros((ncp, nlev), dtype=torch.float64, device=dev)
+    l0 = dm.launch_count()
+    ms = timeit(lambda: dm.difp_device(60.0, dd["atkh"][:ncp], dd["w"][:ncp], rho, dd["detw"], dd["deta"], ffp, fsp))
+    by = ncp * 4900 * (2 * (nlev - 1) + (nlev - 1)) * 8
+    res["difp"] = {"metric": "difp_columns_per_s", "value": ncp * world / (ms * 1e-3), "unit": "columns/s",
+                   "columns_per_gpu": ncp, "levels": nlev, "ms_per_step": ms, "gpu_launches": int(dm.launch_count() - l0),
+                   "tridiagonal_systems_per_s": ncp * 4900 * world / (ms * 1e-3),
+                   "roofline": {"bound": "hbm", "kernel": "difc_solve_kernel<true>", "achieved": by / (ms * 1e-3) * 1e-9,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"],
+                                "peak_source": peak_src, "traffic": None,
+                                "note": "algorithmic bytes per grid point and column = 3*(n-1)*8: every level read and "
+                                        "written once by the solve, read once more by the fsum reduction (%.1f GB of ff: "
+                                        "larger than L2); coefficient, solve and fsum launches timed together"
+                                        % (ncp * nlev * 4900 * 8e-9)}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        m = min(ncp, 32)
+        fh, sh, rh = ffp[:m].cpu().numpy(), fsp[:m].cpu().numpy(), rho[:m].cpu().numpy()
+        reps, t1 = 0, time.perf_counter()
+        while time.perf_counter() - t1 < 3.0:
+            dfo.difp(60.0, dc["atkh"][:m], dc["w"][:m], rh, dc["detw"], dc["deta"], fh, sh)
+            reps += 1
+        dt = time.perf_counter() - t1
+        res["difp"]["cpu_baseline"] = {"value": m * reps / dt, "unit": "columns/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": "%d x %d columns, OpenMP over columns (includes a copy of the arrays), "
+                                                 "%.1f s" % (reps, m, dt)}
+    del dd, ffp, fsp, rho
     # ---- Update_RCONST_a ----
     ens = synthetic.AerEnsemble(max(1, args.cols // 10), seed=20261018 + rank)
     tn = lambda a: None if a is None else t(a)

@@ -161,3 +161,72 @@ module mistra_konc_mod
      end function mistra_konc
   end interface
 end module mistra_konc_mod
+
+! mistra_cwrc_mod / mistra_fastkmt_mod - ISO_C_BINDING interfaces of include/mistra_cwrc.h and
+! include/mistra_fastkmt.h: SUBROUTINE cw_rc (kpp.f90:2152-2414) and SUBROUTINE fast_k_mt_a /
+! fast_k_mt_t (kpp.f90:2683-2947, 2421-2676) for all layers at once, on the COMMON arrays in place.
+module mistra_cwrc_mod
+  use, intrinsic :: iso_c_binding
+  implicit none
+  ! cloud: int32 copy of the LOGICAL cloudt(nkc,k) of /kpp_l1/ (0 = .false.)
+  type, bind(C) :: mistra_cwrc_args
+     integer(c_int32_t) :: nka, nkt, ka, ial
+     real(c_double) :: xcryssulf, xcrysss, xdelisulf, xdeliss
+     type(c_ptr) :: kw, e, rq, ff, feu, cloud, rc, cw, cm, conv2
+  end type mistra_cwrc_args
+  interface
+     function mistra_cwrc(ncell, a, stream) result(rc) bind(C, name="mistra_cwrc")
+       import :: c_int, c_int64_t, c_ptr, mistra_cwrc_args
+       integer(c_int64_t), value :: ncell
+       type(mistra_cwrc_args), intent(in) :: a
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_cwrc
+  end interface
+end module mistra_cwrc_mod
+
+module mistra_fastkmt_mod
+  use, intrinsic :: iso_c_binding
+  implicit none
+  ! lex: int32 copy of the DATA lex(nx) table; xkmt(NSPEC,nkc,k) and vt(nkc,k) are updated in place
+  type, bind(C) :: mistra_fastkmt_args
+     integer(c_int32_t) :: nka, nkt, ka, ial, nkc, nkc_l, nspec, nx
+     type(c_ptr) :: lex, kw, rq, ff, freep, t, p, cw, cm, alpha, vmean, xkmt, vt
+  end type mistra_fastkmt_args
+  interface
+     function mistra_fastkmt(ncell, a, stream) result(rc) bind(C, name="mistra_fastkmt")
+       import :: c_int, c_int64_t, c_ptr, mistra_fastkmt_args
+       integer(c_int64_t), value :: ncell
+       type(mistra_fastkmt_args), intent(in) :: a
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_fastkmt
+  end interface
+end module mistra_fastkmt_mod
+
+! mistra_difc_mod - ISO_C_BINDING interface of include/mistra_difc.h: SUBROUTINE difc
+! (str.f90:3271-3445) on s1, s3, sl1 and sion1 in place; ncol = 1 for the reference's single column.
+module mistra_difc_mod
+  use, intrinsic :: iso_c_binding
+  implicit none
+  integer, parameter :: MISTRA_DIFC_MAXFIELDS = 8
+  type, bind(C) :: mistra_difc_field
+     type(c_ptr) :: s
+     integer(c_int32_t) :: row, nproc
+  end type mistra_difc_field
+  type, bind(C) :: mistra_difc_args
+     integer(c_int32_t) :: n, nfield
+     real(c_double) :: dt
+     type(c_ptr) :: atkh, w, am3, detw, deta
+     type(mistra_difc_field) :: field(MISTRA_DIFC_MAXFIELDS)
+  end type mistra_difc_args
+  interface
+     function mistra_difc(ncol, a, stream) result(rc) bind(C, name="mistra_difc")
+       import :: c_int, c_int64_t, c_ptr, mistra_difc_args
+       integer(c_int64_t), value :: ncol
+       type(mistra_difc_args), intent(in) :: a
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_difc
+  end interface
+end module mistra_difc_mod

@@ -2,16 +2,19 @@
 // entries.  Role in the reference: the layer loop of /root/reference/src/kpp.f90:2820-2945 (and
 // 2558-2674), with FUNCTION vterm (str.f90:2793-2864).
 //
-// Mapping: one persistent CTA (512 threads) per SM, a layer at a time.  The grid tables - radius rqm
-// and the chemistry bin of every grid point (aerosol / droplet part by kw, small / large classes by
-// ka, 255 = not summed) - are put in shared memory once; per layer the 70 x 70 spectrum arrives with
-// 16-byte asynchronous copies.  Pass 1 (a thread per grid point): q = rqm / freep into shared memory
-// and the sedimentation sums (vterm only where ff != 0).  Pass 2: lanes = exchanged species (l and
-// l + 32), warps stride over the grid points, two points per iteration so that every thread has four
-// independent FP64 divisions in flight; each thread keeps its species' sums of the four bins in
-// registers.  Points with ff == 0 and points of a bin without chemistry (cm <= 0) add exactly +0 in
-// the reference and are skipped.  Partial sums are combined over the warps in warp order.
-// FP64-bound: (nx + 1) divisions per populated grid point against 39.2 kB read per layer.
+// Mapping: one persistent CTA (512 threads) per SM, a layer at a time, the next layer's 70 x 70
+// spectrum arriving by 16-byte asynchronous copies into the second half of a double buffer while the
+// current one is integrated.  The grid tables - radius rqm and the chemistry bin of every grid point
+// (aerosol / droplet part by kw, small / large classes by ka, 255 = not summed) - are put in shared
+// memory once.  Per layer: (1) the grid points that contribute are compacted, in grid order, into two
+// index lists (ballot + prefix over the warps): points with ff != 0 for the sedimentation sums, and
+// those of them whose bin has chemistry (cm > 0) for the transfer coefficients - every other point
+// adds exactly +0 in the reference; (2) a thread per listed point: q = rqm / freep and the vterm
+// term; (3) lanes = exchanged species (l and l + 32), warps stride over the listed points, three
+// points per iteration so that every thread has six independent FP64 divisions in flight; each
+// thread keeps its species' sums of the four bins in registers.  Partial sums are combined over the
+// warps in warp order.  Real spectra populate a few per cent of the grid, then the kernel streams
+// ff (39.2 kB per layer); with every point populated it is FP64-bound: (nx + 1) divisions per point.
 // No FMA contraction (build.py).
 #include "../../include/mistra_fastkmt.h"
 #include "../../include/mistra_kpp.h"
@@ -73,49 +76,77 @@ __device__ __forceinline__ double vterm(double a, double t, double p)
     }                                                                       \
   } while (0)
 
+struct FkSmem {
+  double *f0, *r, *q, *red, *vt;      // f0: [2][npad]
+  int npad;
+  unsigned short *l1, *l2;
+  unsigned char *kc;
+  int *cnt;
+};
+
+__device__ __forceinline__ FkSmem fk_carve(double *smem, int ntile)
+{
+  const int npad = (ntile + 1) & ~1, lpad = (ntile + 7) & ~7;
+  FkSmem s;
+  s.npad = npad;
+  s.f0 = smem;                              // [2][npad]: the layer's spectrum, double-buffered
+  s.r = s.f0 + 2 * npad;                     // [ntile] rqm = rq * 1e-6 (kpp.f90:2806)
+  s.q = s.r + npad;                         // [n2] rqm / freep(k) of the points of list 2
+  s.red = s.q + npad;                       // [FK_WARPS][FK_NKC][64] partial sums of the transfer coefficients
+  s.vt = s.red + FK_WARPS * FK_NKC * 64;    // [FK_WARPS][FK_NKC]
+  s.l1 = (unsigned short *)(s.vt + FK_WARPS * FK_NKC);   // points with ff != 0 (sedimentation sums)
+  s.l2 = s.l1 + lpad;                       // ... whose bin has chemistry (transfer coefficients)
+  s.kc = (unsigned char *)(s.l2 + lpad);    // [ntile] bin of the point, 255 = none
+  s.cnt = (int *)(s.kc + lpad);             // [2][FK_WARPS] list lengths per warp
+  return s;
+}
+
+__device__ __forceinline__ void fk_fetch(double *dst, const double *gf, int ntile)
+{
+  if ((ntile & 1) == 0) {
+    for (int q = threadIdx.x; q < (ntile >> 1); q += FK_THREADS)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst + 2 * q)),
+                   "l"(gf + 2 * q) : "memory");
+  } else {
+    for (int q = threadIdx.x; q < ntile; q += FK_THREADS)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst + q)),
+                   "l"(gf + q) : "memory");
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
 __global__ void __launch_bounds__(FK_THREADS, 1) fastkmt_kernel(long long ncell, mistra_fastkmt_args a)
 {
   extern __shared__ __align__(16) double smem[];
-  const int nka = a.nka, nkt = a.nkt, ntile = nka * nkt, npad = (ntile + 1) & ~1;
-  double *s_f = smem;                       // [ntile] the layer's spectrum
-  double *s_r = s_f + npad;                 // [ntile] rqm = rq * 1e-6 (kpp.f90:2806)
-  double *s_q = s_r + npad;                 // [ntile] rqm / freep(k)
-  double *s_red = s_q + npad;               // [FK_WARPS][FK_NKC][64] partial sums of pass 2
-  double *s_vt = s_red + FK_WARPS * FK_NKC * 64;   // [FK_WARPS][FK_NKC]
-  unsigned char *s_kc = (unsigned char *)(s_vt + FK_WARPS * FK_NKC);   // [ntile] bin of the point, 255 = none
+  const int nka = a.nka, nkt = a.nkt, ntile = nka * nkt;
+  const FkSmem s = fk_carve(smem, ntile);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double z4pi3 = 4.0 * 3.1415926535897932 / 3.0;   // kpp.f90:2758
   const int nx = a.nx, nspec = a.nspec, nkc = a.nkc;
 
+  if ((long long)blockIdx.x < ncell) fk_fetch(s.f0, a.ff + (size_t)blockIdx.x * ntile, ntile);
   for (int q = threadIdx.x; q < ntile; q += FK_THREADS) {
     const int ia = q / nkt, jt = q - ia * nkt;
-    s_r[q] = a.rq[q] * 1.e-6;
+    s.r[q] = a.rq[q] * 1.e-6;
     int kc = (jt < a.kw[ia] ? 0 : 2) + (ia < a.ka ? 0 : 1);          // kpp.f90:2869-2901
     if (kc >= a.nkc_l || (ia < a.ial - 1 && ia < a.ka)) kc = 255;    // ifeed == 2 drops the first small class
-    s_kc[q] = (unsigned char)kc;
+    s.kc[q] = (unsigned char)kc;
   }
   const int l0 = lane, l1 = lane + 32;
   const int sp0 = l0 < nx ? a.lex[l0] - 1 : -1, sp1 = l1 < nx ? a.lex[l1] - 1 : -1;
 
-  for (long long c = blockIdx.x; c < ncell; c += gridDim.x) {
-    __syncthreads();
-    const double *gf = a.ff + (size_t)c * ntile;
-    if ((ntile & 1) == 0) {
-      for (int q = threadIdx.x; q < (ntile >> 1); q += FK_THREADS)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(s_f + 2 * q)),
-                     "l"(gf + 2 * q) : "memory");
-    } else {
-      for (int q = threadIdx.x; q < ntile; q += FK_THREADS)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(s_f + q)),
-                     "l"(gf + q) : "memory");
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  int buf = 0;
+  for (long long c = blockIdx.x; c < ncell; c += gridDim.x, buf ^= 1) {
+    __syncthreads();                         // the other buffer, the lists and the partial sums are free again
+    const long long cn = c + gridDim.x;
+    if (cn < ncell) fk_fetch(s.f0 + (buf ^ 1) * s.npad, a.ff + (size_t)cn * ntile, ntile);
     // layer scalars while the tile is in flight
     const double freep = a.freep[c], tk = a.t[c], pk = a.p[c];
     unsigned onmask = 0;                     // bins with chemistry (cm > 0, kpp.f90:2826)
     for (int kc = 0; kc < a.nkc_l; ++kc)
       if (a.cm[c * nkc + kc] > 0.0) onmask |= 1u << kc;
-    double vm0 = 0.0, vm1 = 0.0, x10 = 1.0, x11 = 1.0;     // idle lanes: 0 / (q + 1)
+    double vm0 = 1.0, vm1 = 1.0, x10 = 1.0, x11 = 1.0;     // idle lanes: 1 / (q + 1), never stored (a zero
+                                                           // numerator would send the whole warp down the slow path of the division)
     if (sp0 >= 0) {
       const double al = a.alpha[c * nspec + sp0];
       vm0 = a.vmean[c * nspec + sp0];
@@ -126,57 +157,76 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fastkmt_kernel(long long ncell,
       vm1 = a.vmean[c * nspec + sp1];
       x11 = (al > 0.0) ? 4. / (3. * al) : 0.0;
     }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    if (cn < ncell) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    else            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
+    const double *sf = s.f0 + buf * s.npad;
 
-    // pass 1: q = rqm / freep, sedimentation sums (kpp.f90:2924-2927)
+    // (1) compaction in grid order
+    int n1 = 0, n2 = 0;
+    for (int base = 0; base < ntile; base += FK_THREADS) {
+      const int q = base + threadIdx.x;
+      bool act1 = false, act2 = false;
+      if (q < ntile) {
+        const int kc = s.kc[q];
+        act1 = kc != 255 && sf[q] != 0.0;
+        act2 = act1 && ((onmask >> kc) & 1u);
+      }
+      const unsigned b1 = __ballot_sync(0xffffffffu, act1), b2 = __ballot_sync(0xffffffffu, act2);
+      if (lane == 0) { s.cnt[warp] = __popc(b1); s.cnt[FK_WARPS + warp] = __popc(b2); }
+      __syncthreads();
+      int o1 = n1, o2 = n2;
+#pragma unroll
+      for (int w = 0; w < FK_WARPS; ++w) {
+        const int c1 = s.cnt[w], c2 = s.cnt[FK_WARPS + w];
+        if (w < warp) { o1 += c1; o2 += c2; }
+        n1 += c1; n2 += c2;
+      }
+      const unsigned below = (1u << lane) - 1u;
+      if (act1) s.l1[o1 + __popc(b1 & below)] = (unsigned short)q;
+      if (act2) s.l2[o2 + __popc(b2 & below)] = (unsigned short)q;
+      __syncthreads();
+    }
+
+    // (2) q = rqm / freep of list 2; sedimentation sums over list 1 (kpp.f90:2924-2927)
+    for (int i = threadIdx.x; i < n2; i += FK_THREADS) s.q[i] = s.r[s.l2[i]] / freep;
     {
       double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-      for (int q = threadIdx.x; q < ntile; q += FK_THREADS) {
-        const double rqq = s_r[q], f = s_f[q];
-        s_q[q] = rqq / freep;
-        const int kc = s_kc[q];
-        if (kc != 255 && f != 0.0) {
-          const double xvs = vterm(rqq, tk, pk);
-          const double term = rqq * rqq * rqq * xvs * f * 1.e6;
-          if (kc == 0) v0 = v0 + term; else if (kc == 1) v1 = v1 + term; else if (kc == 2) v2 = v2 + term; else v3 = v3 + term;
-        }
+      for (int i = threadIdx.x; i < n1; i += FK_THREADS) {
+        const int q = s.l1[i];
+        const double rqq = s.r[q];
+        const double xvs = vterm(rqq, tk, pk);
+        const double term = rqq * rqq * rqq * xvs * sf[q] * 1.e6;
+        const int kc = s.kc[q];
+        if (kc == 0) v0 = v0 + term; else if (kc == 1) v1 = v1 + term; else if (kc == 2) v2 = v2 + term; else v3 = v3 + term;
       }
       v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
-      if (lane == 0) { s_vt[warp * 4 + 0] = v0; s_vt[warp * 4 + 1] = v1; s_vt[warp * 4 + 2] = v2; s_vt[warp * 4 + 3] = v3; }
+      if (lane == 0) { s.vt[warp * 4 + 0] = v0; s.vt[warp * 4 + 1] = v1; s.vt[warp * 4 + 2] = v2; s.vt[warp * 4 + 3] = v3; }
     }
     __syncthreads();
 
-    // pass 2: transfer coefficients (kpp.f90:2913-2922); warp-uniform control flow
-    double a00 = 0.0, a01 = 0.0, a02 = 0.0, a03 = 0.0, a10 = 0.0, a11 = 0.0, a12 = 0.0, a13 = 0.0;
-    if (onmask) {
-      for (int q = warp; q < ntile; q += 2 * FK_WARPS) {
-        const int qb = q + FK_WARPS;
-        const int kcA = s_kc[q], kcB = qb < ntile ? s_kc[qb] : 255;
-        const double fA = s_f[q], fB = qb < ntile ? s_f[qb] : 0.0;
-        const bool actA = kcA != 255 && ((onmask >> kcA) & 1u) && fA != 0.0;
-        const bool actB = kcB != 255 && ((onmask >> kcB) & 1u) && fB != 0.0;
-        if (actA && actB) {
-          const double rA = s_r[q], qA = s_q[q], rB = s_r[qb], qB = s_q[qb];
-          const double xA0 = vm0 / (qA + x10), xA1 = vm1 / (qA + x11);
-          const double xB0 = vm0 / (qB + x10), xB1 = vm1 / (qB + x11);
-          const double tA0 = xA0 * rA * rA * fA * 1.e6, tA1 = xA1 * rA * rA * fA * 1.e6;
-          const double tB0 = xB0 * rB * rB * fB * 1.e6, tB1 = xB1 * rB * rB * fB * 1.e6;
-          FK_ACC(kcA, tA0, tA1);
-          FK_ACC(kcB, tB0, tB1);
-        } else if (actA) {
-          const double rA = s_r[q], qA = s_q[q];
-          const double xA0 = vm0 / (qA + x10), xA1 = vm1 / (qA + x11);
-          const double tA0 = xA0 * rA * rA * fA * 1.e6, tA1 = xA1 * rA * rA * fA * 1.e6;
-          FK_ACC(kcA, tA0, tA1);
-        } else if (actB) {
-          const double rB = s_r[qb], qB = s_q[qb];
-          const double xB0 = vm0 / (qB + x10), xB1 = vm1 / (qB + x11);
-          const double tB0 = xB0 * rB * rB * fB * 1.e6, tB1 = xB1 * rB * rB * fB * 1.e6;
-          FK_ACC(kcB, tB0, tB1);
-        }
+    // (3) transfer coefficients (kpp.f90:2913-2922); warp-uniform control flow
+    if (n2 > 0) {
+      double a00 = 0.0, a01 = 0.0, a02 = 0.0, a03 = 0.0, a10 = 0.0, a11 = 0.0, a12 = 0.0, a13 = 0.0;
+      for (int i = warp; i < n2; i += 3 * FK_WARPS) {
+        const int ib = i + FK_WARPS, ic = i + 2 * FK_WARPS;
+        const bool vb = ib < n2, vc = ic < n2;
+        const int pA = s.l2[i], pB = vb ? s.l2[ib] : pA, pC = vc ? s.l2[ic] : pA;
+        const double fA = sf[pA], fB = vb ? sf[pB] : 0.0, fC = vc ? sf[pC] : 0.0;    // a missing point adds +0
+        const double rA = s.r[pA], rB = s.r[pB], rC = s.r[pC];
+        const double qA = s.q[i], qB = s.q[vb ? ib : i], qC = s.q[vc ? ic : i];
+        const int kcA = s.kc[pA], kcB = s.kc[pB], kcC = s.kc[pC];
+        const double xA0 = vm0 / (qA + x10), xA1 = vm1 / (qA + x11);
+        const double xB0 = vm0 / (qB + x10), xB1 = vm1 / (qB + x11);
+        const double xC0 = vm0 / (qC + x10), xC1 = vm1 / (qC + x11);
+        const double tA0 = xA0 * rA * rA * fA * 1.e6, tA1 = xA1 * rA * rA * fA * 1.e6;
+        const double tB0 = xB0 * rB * rB * fB * 1.e6, tB1 = xB1 * rB * rB * fB * 1.e6;
+        const double tC0 = xC0 * rC * rC * fC * 1.e6, tC1 = xC1 * rC * rC * fC * 1.e6;
+        FK_ACC(kcA, tA0, tA1);
+        FK_ACC(kcB, tB0, tB1);
+        FK_ACC(kcC, tC0, tC1);
       }
-      double *r = s_red + warp * (FK_NKC * 64);
+      double *r = s.red + warp * (FK_NKC * 64);
       r[0 * 64 + l0] = a00; r[1 * 64 + l0] = a01; r[2 * 64 + l0] = a02; r[3 * 64 + l0] = a03;
       r[0 * 64 + l1] = a10; r[1 * 64 + l1] = a11; r[2 * 64 + l1] = a12; r[3 * 64 + l1] = a13;
     }
@@ -188,9 +238,10 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fastkmt_kernel(long long ncell,
       if (kc < a.nkc_l && l < nx && ((onmask >> kc) & 1u)) {
         const double cw = a.cw[c * nkc + kc];
         if (cw > 0.0) {
-          double s = 0.0;
-          for (int w = 0; w < FK_WARPS; ++w) s = s + s_red[w * (FK_NKC * 64) + kc * 64 + l];
-          a.xkmt[((size_t)c * nkc + kc) * nspec + a.lex[l] - 1] = z4pi3 / cw * s;
+          double sum = 0.0;
+          if (n2 > 0)
+            for (int w = 0; w < FK_WARPS; ++w) sum = sum + s.red[w * (FK_NKC * 64) + kc * 64 + l];
+          a.xkmt[((size_t)c * nkc + kc) * nspec + a.lex[l] - 1] = z4pi3 / cw * sum;
         }
       }
     } else if (threadIdx.x < FK_NKC * 64 + FK_NKC) {
@@ -198,9 +249,9 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fastkmt_kernel(long long ncell,
       if (kc < a.nkc_l) {
         const double cw = a.cw[c * nkc + kc];
         if (cw > 0.0) {
-          double s = 0.0;
-          for (int w = 0; w < FK_WARPS; ++w) s = s + s_vt[w * 4 + kc];
-          a.vt[c * nkc + kc] = z4pi3 / cw * s;
+          double sum = 0.0;
+          for (int w = 0; w < FK_WARPS; ++w) sum = sum + s.vt[w * 4 + kc];
+          a.vt[c * nkc + kc] = z4pi3 / cw * sum;
         }
       }
     }
@@ -243,8 +294,9 @@ int check(int64_t ncell, const mistra_fastkmt_args *a)
 
 size_t smem_bytes(const mistra_fastkmt_args *a)
 {
-  const size_t ntile = (size_t)a->nka * a->nkt, npad = (ntile + 1) & ~(size_t)1;
-  return sizeof(double) * (3 * npad + FK_WARPS * FK_NKC * 64 + FK_WARPS * FK_NKC) + ((ntile + 15) & ~(size_t)15);
+  const size_t ntile = (size_t)a->nka * a->nkt, npad = (ntile + 1) & ~(size_t)1, lpad = (ntile + 7) & ~(size_t)7;
+  return sizeof(double) * (4 * npad + FK_WARPS * FK_NKC * 64 + FK_WARPS * FK_NKC) + 2 * 2 * lpad + lpad +
+         sizeof(int) * 2 * FK_WARPS;
 }
 
 }  // namespace
@@ -261,9 +313,10 @@ int mistra_fastkmt_device(int64_t ncell, const mistra_fastkmt_args *d_a, void *s
   if (dev < 0 || dev >= 16) return mistra_internal_fail(MISTRA_KPP_ENODEVICE, "device index out of range");
   CKW(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t smem = smem_bytes(d_a);
-  if (smem > 220 * 1024) return mistra_internal_fail(MISTRA_KPP_EINVAL, "particle grid too large for shared memory");
+  if (smem > 226 * 1024 || (size_t)d_a->nka * d_a->nkt > 65535)
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "particle grid too large for shared memory (nka * nkt <= ~5300)");
   if (!g_attr[dev]) {
-    CKW(cudaFuncSetAttribute(fastkmt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CKW(cudaFuncSetAttribute(fastkmt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     g_attr[dev] = true;
   }
   long long blocks = sms;
