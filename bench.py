@@ -789,16 +789,16 @@ def run_next_rows_leg(args, dev, world, rank, barrier):
     fsp = torch.zeros((ncp, nlev), dtype=torch.float64, device=dev)
     l0 = dm.launch_count()
     ms = timeit(lambda: dm.difp_device(60.0, dd["atkh"][:ncp], dd["w"][:ncp], rho, dd["detw"], dd["deta"], ffp, fsp))
-    by = ncp * 4900 * (2 * (nlev - 1) + (nlev - 1)) * 8
+    by = ncp * 4900 * 2 * (nlev - 1) * 8
     res["difp"] = {"metric": "difp_columns_per_s", "value": ncp * world / (ms * 1e-3), "unit": "columns/s",
                    "columns_per_gpu": ncp, "levels": nlev, "ms_per_step": ms, "gpu_launches": int(dm.launch_count() - l0),
                    "tridiagonal_systems_per_s": ncp * 4900 * world / (ms * 1e-3),
                    "roofline": {"bound": "hbm", "kernel": "difc_solve_kernel<true>", "achieved": by / (ms * 1e-3) * 1e-9,
                                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"],
                                 "peak_source": peak_src, "traffic": None,
-                                "note": "algorithmic bytes per grid point and column = 3*(n-1)*8: every level read and "
-                                        "written once by the solve, read once more by the fsum reduction (%.1f GB of ff: "
-                                        "larger than L2); coefficient, solve and fsum launches timed together"
+                                "note": "algorithmic bytes per grid point and column = 2*(n-1)*8: every level read and "
+                                        "written once (the level sums fsum ride along in the backward sweep); %.1f GB of ff: "
+                                        "larger than L2; coefficient, solve and fsum launches timed together"
                                         % (ncp * nlev * 4900 * 8e-9)}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         m = min(ncp, 32)

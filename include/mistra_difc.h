@@ -58,8 +58,9 @@ int mistra_difc_device(int64_t ncol, const mistra_difc_args *d_a, void *stream);
  * followed by fsum(k) = sum of ff(:,:,k) for k = 2..n.
  *   ff [ncol][n][row] IN/OUT, row = nka * nkt  COMMON /cb52/     rho [ncol][n]  COMMON /cb53/
  *   fsum [ncol][n]    IN/OUT (level 1 untouched)
- * ff is bit-identical to the reference order; fsum is a sum of row non-negative terms formed as 256
- * interleaved partial sums (the reference keeps one running sum): ~1e-14 relative (tests: 1e-13). */
+ * ff is bit-identical to the reference order; fsum is a sum of row non-negative terms formed per group
+ * of 128 consecutive grid points (butterfly over the lanes, warps in order) and then over the groups in
+ * order (the reference keeps one running sum): ~1e-14 relative (tests: 1e-13). */
 typedef struct mistra_difp_args {
   int32_t n, row;
   double dt;

@@ -29,7 +29,6 @@ namespace {
 
 constexpr int DIFC_THREADS = 128;
 constexpr int DIFC_MAXN = 512;
-constexpr int DIFC_U = 8;       // levels per batch of the sweeps
 
 // coef [ncol][4][n]: xc, xd, xe, c (index 0 of each unused, as in the reference).  One warp per
 // column: xa, xc, xb and c do not depend on the recurrence and are formed by all lanes (coalesced
@@ -78,6 +77,16 @@ __global__ void __launch_bounds__(COEF_WARPS * 32) difc_coef_kernel(long long nc
   for (int k = lane; k <= nm; k += 32) { o[k] = xc[k]; o[n + k] = xd[k]; o[2 * n + k] = xe[k]; }
 }
 
+// x / d for d > 0 and finite (air density, the pivots xd >= 1): a zero numerator is returned as it is -
+// IEEE gives exactly that, sign of the zero included - without entering the division, whose slow path
+// (taken by the whole warp as soon as one lane holds a zero) would otherwise run for every empty bin of
+// a sparse spectrum.  Any other d goes through the division.
+__device__ __forceinline__ double div_pos(double x, double d)
+{
+  if (x == 0.0 && d > 0.0 && d <= 1.7976931348623157e308) return x;
+  return x / d;
+}
+
 struct DifcFields {                                        // the species of all arrays as one virtual row
   double *s[MISTRA_DIFC_MAXFIELDS];
   int row[MISTRA_DIFC_MAXFIELDS], first[MISTRA_DIFC_MAXFIELDS + 1];
@@ -87,48 +96,50 @@ struct DifcFields {                                        // the species of all
 // DIFP = false: difc (species amounts s, mixing ratio s / am3).  DIFP = true: difp (str.f90:3137-3265):
 // the particle spectrum is divided by rho at every level first (top level included, which therefore
 // is rewritten as ff / rho * rho), the recurrences run on the ratio, the subsidence on the product.
-template <bool DIFP>
+template <bool DIFP, int DIFC_U>
 __global__ void __launch_bounds__(DIFC_THREADS) difc_solve_kernel(int n, const double *__restrict__ coef,
-                                                                  const double *__restrict__ am3, DifcFields fl)
+                                                                  const double *__restrict__ am3, DifcFields fl,
+                                                                  double *__restrict__ partial)
 {
-  extern __shared__ double sm[];                           // xc, xd, xe, c, am3 of the column: [5][n]
+  extern __shared__ double sm[];                           // xc, xd, xe, c, am3 of the column: [5][n]; DIFP: + [4][n]
   const long long col = blockIdx.y;
   const double *cf = coef + col * 4 * n;
   for (int q = threadIdx.x; q < 4 * n; q += DIFC_THREADS) sm[q] = cf[q];
   for (int q = threadIdx.x; q < n; q += DIFC_THREADS) sm[4 * n + q] = am3[col * n + q];
   __syncthreads();
   const int j = blockIdx.x * DIFC_THREADS + threadIdx.x;
-  if (j >= fl.first[fl.nfield]) return;
+  const bool act = j < fl.first[fl.nfield];
+  if (!DIFP && !act) return;                               // DIFP: idle lanes stay for the level sums (they add 0)
   int f = 0;
 #pragma unroll
   for (int q = 1; q < MISTRA_DIFC_MAXFIELDS; ++q)
     if (q < fl.nfield && j >= fl.first[q]) f = q;
   const int row = fl.row[f];
   const double *xc = sm, *xd = sm + n, *xe = sm + 2 * n, *c = sm + 3 * n, *am = sm + 4 * n;
-  double *s = fl.s[f] + (size_t)col * n * row + (j - fl.first[f]);
+  double *s = fl.s[f] + (size_t)col * n * row + (act ? j - fl.first[f] : 0);
   const int nm = n - 1;
   // The sweeps run in batches of DIFC_U levels: the loads of the next batch are issued before the
   // dependent arithmetic and the stores of the current one (the stores may alias as far as the
   // compiler knows), so a thread waits for memory once per batch instead of once per level.
   double v[DIFC_U], vn[DIFC_U];
-  double xf = s[(size_t)row] / am[1];                      // xf(1) = s(j,2)/am3(2)
+  double xf = div_pos(act ? s[(size_t)row] : 1.0, am[1]);  // xf(1) = s(j,2)/am3(2)
 #pragma unroll
-  for (int i = 0; i < DIFC_U; ++i) v[i] = (1 + i < nm) ? s[(size_t)(1 + i) * row] : 0.0;
+  for (int i = 0; i < DIFC_U; ++i) v[i] = (act && 1 + i < nm) ? s[(size_t)(1 + i) * row] : 1.0;
   for (int k = 1; k < nm; k += DIFC_U) {                   // forward elimination, str.f90:3348-3350 / 3230-3232
 #pragma unroll
-    for (int i = 0; i < DIFC_U; ++i) vn[i] = (k + DIFC_U + i < nm) ? s[(size_t)(k + DIFC_U + i) * row] : 0.0;
+    for (int i = 0; i < DIFC_U; ++i) vn[i] = (act && k + DIFC_U + i < nm) ? s[(size_t)(k + DIFC_U + i) * row] : 1.0;
 #pragma unroll
     for (int i = 0; i < DIFC_U; ++i)
       if (k + i < nm) {
-        xf = (v[i] / am[k + i] + xc[k + i] * xf) / xd[k + i];
-        s[(size_t)(k + i) * row] = xf;
+        xf = div_pos(div_pos(v[i], am[k + i]) + xc[k + i] * xf, xd[k + i]);
+        if (act) s[(size_t)(k + i) * row] = xf;
       }
 #pragma unroll
     for (int i = 0; i < DIFC_U; ++i) v[i] = vn[i];
   }
   // backward: levels nm-1 .. 1; v[i] = xf(k - i)
 #pragma unroll
-  for (int i = 0; i < DIFC_U; ++i) v[i] = (nm - 1 - i >= 1) ? s[(size_t)(nm - 1 - i) * row] : 0.0;
+  for (int i = 0; i < DIFC_U; ++i) v[i] = (act && nm - 1 - i >= 1) ? s[(size_t)(nm - 1 - i) * row] : 1.0;
   if (!DIFP) {
     double up = s[(size_t)nm * row];                       // s(j,n): boundary value, diffused value of level k+1 below
     for (int k = nm - 1; k >= 1; k -= DIFC_U) {            // back substitution 3351-3353 + subsidence 3354-3356
@@ -137,7 +148,7 @@ __global__ void __launch_bounds__(DIFC_THREADS) difc_solve_kernel(int n, const d
 #pragma unroll
       for (int i = 0; i < DIFC_U; ++i)
         if (k - i >= 1) {
-          const double sd = (xe[k - i] * up / am[k - i + 1] + v[i]) * am[k - i];
+          const double sd = (div_pos(xe[k - i] * up, am[k - i + 1]) + v[i]) * am[k - i];
           s[(size_t)(k - i) * row] = sd - c[k - i] * (up - sd);
           up = sd;
         }
@@ -145,44 +156,58 @@ __global__ void __launch_bounds__(DIFC_THREADS) difc_solve_kernel(int n, const d
       for (int i = 0; i < DIFC_U; ++i) v[i] = vn[i];
     }
   } else {
-    double upr = s[(size_t)nm * row] / am[nm];             // ff(n) / rho(n), 3210-3212
+    // fsum(k), str.f90:3248-3255: the level sums of this CTA's grid points ride along - a fixed butterfly
+    // over the lanes per level, the four warps in order below, the CTAs in order in difp_fsum_kernel
+    double *s_part = sm + 5 * n;                           // [4 warps][n]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double upr = div_pos(act ? s[(size_t)nm * row] : 1.0, am[nm]);   // ff(n) / rho(n), 3210-3212
     double upm = upr * am[nm];                             // ... * rho(n), 3238-3240
-    s[(size_t)nm * row] = upm;
+    if (act) s[(size_t)nm * row] = upm;
+    {
+      double w = act ? upm : 0.0;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) w = w + __shfl_xor_sync(0xffffffffu, w, off);
+      if (lane == 0) s_part[warp * n + nm] = w;
+    }
     for (int k = nm - 1; k >= 1; k -= DIFC_U) {            // 3234-3236, 3238-3240, 3243-3246
 #pragma unroll
-      for (int i = 0; i < DIFC_U; ++i) vn[i] = (k - DIFC_U - i >= 1) ? s[(size_t)(k - DIFC_U - i) * row] : 0.0;
+      for (int i = 0; i < DIFC_U; ++i) vn[i] = (act && k - DIFC_U - i >= 1) ? s[(size_t)(k - DIFC_U - i) * row] : 1.0;
 #pragma unroll
       for (int i = 0; i < DIFC_U; ++i)
         if (k - i >= 1) {
           const double xr = xe[k - i] * upr + v[i];
           const double sp = xr * am[k - i];
-          s[(size_t)(k - i) * row] = sp - c[k - i] * (upm - sp);
+          const double fin = sp - c[k - i] * (upm - sp);
+          if (act) s[(size_t)(k - i) * row] = fin;
           upr = xr; upm = sp;
+          double w = act ? fin : 0.0;
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) w = w + __shfl_xor_sync(0xffffffffu, w, off);
+          if (lane == 0) s_part[warp * n + k - i] = w;
         }
 #pragma unroll
       for (int i = 0; i < DIFC_U; ++i) v[i] = vn[i];
     }
+    __syncthreads();
+    double *po = partial + ((size_t)col * gridDim.x + blockIdx.x) * n;
+    for (int k = 1 + threadIdx.x; k <= nm; k += DIFC_THREADS) {
+      double t = s_part[k];
+#pragma unroll
+      for (int q = 1; q < DIFC_THREADS / 32; ++q) t = t + s_part[q * n + k];
+      po[k] = t;
+    }
   }
 }
 
-// fsum(k) = sum of the spectrum of level k (str.f90:3248-3255): one CTA per (level, column); per-thread
-// strided partial sums, a fixed butterfly over the lanes, then the warps in order (the reference keeps
-// one running sum over the nka * nkt points).
-__global__ void __launch_bounds__(256) difp_fsum_kernel(int n, const double *__restrict__ ff, int row, double *fsum)
+// fsum(k) = sum over the CTAs of a column of their level sums, in CTA order (str.f90:3248-3255; the
+// reference keeps one running sum over the nka * nkt points).
+__global__ void __launch_bounds__(128) difp_fsum_kernel(int n, int nblk, const double *__restrict__ partial, double *fsum)
 {
-  __shared__ double s_w[8];
-  const long long col = blockIdx.y;
-  const int k = blockIdx.x + 1;
-  const double *f = ff + ((size_t)col * n + k) * row;
-  double v = 0.0;
-  for (int q = threadIdx.x; q < row; q += 256) v = v + f[q];
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
-  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < 8; ++w) t = t + s_w[w];
+  const long long col = blockIdx.x;
+  for (int k = 1 + threadIdx.x; k < n; k += 128) {
+    const double *p = partial + (size_t)col * nblk * n + k;
+    double t = p[0];
+    for (int b = 1; b < nblk; ++b) t = t + p[(size_t)b * n];
     fsum[col * n + k] = t;
   }
 }
@@ -212,16 +237,18 @@ size_t solve_smem(int n)
     const int v = e ? atoi(e) : 16;
     return v < 1 ? 1 : (v > 16 ? 16 : v);
   }();
-  const size_t need = 5 * (size_t)n * sizeof(double), cap = (size_t)(224 * 1024) / resident - 1024;
+  const size_t need = 9 * (size_t)n * sizeof(double), cap = (size_t)(224 * 1024) / resident - 1024;
   return need > cap ? need : cap;
 }
+
+constexpr int DIFC_BATCH = 8;    // levels per batch of the sweeps (16 measured slower: 96 registers, 5 CTAs per SM)
 
 bool g_attr[16] = {};
 int set_attrs(int dev)
 {
   if (g_attr[dev]) return 0;
-  CKW(cudaFuncSetAttribute(difc_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-  CKW(cudaFuncSetAttribute(difc_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  CKW(cudaFuncSetAttribute(difc_solve_kernel<false, DIFC_BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  CKW(cudaFuncSetAttribute(difc_solve_kernel<true, DIFC_BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   CKW(cudaFuncSetAttribute(difc_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   g_attr[dev] = true;
   return 0;
@@ -287,7 +314,8 @@ int mistra_difc_device(int64_t ncol, const mistra_difc_args *d_a, void *stream)
     DifcFields fc = fl;
     for (int f = 0; f < fl.nfield; ++f) fc.s[f] = fl.s[f] + (size_t)c0 * n * fl.row[f];
     dim3 grid((fl.first[fl.nfield] + DIFC_THREADS - 1) / DIFC_THREADS, (unsigned)nc);
-    difc_solve_kernel<false><<<grid, DIFC_THREADS, solve_smem(n), st>>>(n, coef + c0 * 4 * n, d_a->am3 + c0 * n, fc);
+    difc_solve_kernel<false, DIFC_BATCH><<<grid, DIFC_THREADS, solve_smem(n), st>>>(n, coef + c0 * 4 * n, d_a->am3 + c0 * n,
+                                                                                   fc, nullptr);
     CKW(cudaGetLastError());
     g_launches.fetch_add(1);
   }
@@ -350,27 +378,30 @@ int mistra_difp_device(int64_t ncol, const mistra_difp_args *d_a, void *stream)
   cudaStream_t st = (cudaStream_t)stream;
   const int n = d_a->n;
   if (int rca = set_attrs(dev)) return rca;
-  const size_t need = (size_t)ncol * 4 * n * sizeof(double);
+  const size_t nblk = ((size_t)d_a->row + DIFC_THREADS - 1) / DIFC_THREADS;
+  const size_t ncmax = ncol < 65535 ? (size_t)ncol : 65535;
+  const size_t need = ((size_t)ncol * 4 * n + ncmax * nblk * n) * sizeof(double);   // coefficients + level sums per CTA
   Scratch &cf = g_coef[dev];
   if (cf.bytes < need) {
     if (cf.p) { CKW(cudaDeviceSynchronize()); cudaFree(cf.p); cf.p = nullptr; cf.bytes = 0; }
     CKW(cudaMalloc(&cf.p, need));
     cf.bytes = need;
   }
-  double *coef = (double *)cf.p;
+  double *coef = (double *)cf.p, *partial = coef + (size_t)ncol * 4 * n;
   difc_coef_kernel<<<(unsigned)((ncol + COEF_WARPS - 1) / COEF_WARPS), COEF_WARPS * 32, COEF_WARPS * 5 * n * sizeof(double),
                      st>>>(ncol, n, d_a->dt, d_a->atkh, d_a->w, d_a->detw, d_a->deta, coef);
   CKW(cudaGetLastError());
   g_launches.fetch_add(1);
   for (int64_t c0 = 0; c0 < ncol; c0 += 65535) {           // grid.y limit
     const int64_t nc = ncol - c0 < 65535 ? ncol - c0 : 65535;
-    dim3 grid((d_a->row + DIFC_THREADS - 1) / DIFC_THREADS, (unsigned)nc);
+    dim3 grid((unsigned)nblk, (unsigned)nc);
     double *ffc = d_a->ff + (size_t)c0 * n * d_a->row;
     DifcFields fc;
     fc.nfield = 1; fc.s[0] = ffc; fc.row[0] = d_a->row; fc.first[0] = 0; fc.first[1] = d_a->row;
-    difc_solve_kernel<true><<<grid, DIFC_THREADS, solve_smem(n), st>>>(n, coef + c0 * 4 * n, d_a->rho + c0 * n, fc);
+    difc_solve_kernel<true, DIFC_BATCH><<<grid, DIFC_THREADS, solve_smem(n), st>>>(n, coef + c0 * 4 * n, d_a->rho + c0 * n,
+                                                                                  fc, partial);
     CKW(cudaGetLastError());
-    difp_fsum_kernel<<<dim3(n - 1, (unsigned)nc), 256, 0, st>>>(n, ffc, d_a->row, d_a->fsum + c0 * n);
+    difp_fsum_kernel<<<(unsigned)nc, 128, 0, st>>>(n, (int)grid.x, partial, d_a->fsum + c0 * n);
     CKW(cudaGetLastError());
     g_launches.fetch_add(2);
   }

@@ -77,7 +77,7 @@ __device__ __forceinline__ double vterm(double a, double t, double p)
   } while (0)
 
 struct FkSmem {
-  double *f0, *r, *q, *red, *vt;      // f0: [2][npad]
+  double *f0, *r, *q, *red, *vt, *sc;      // f0: [2][npad]
   int npad;
   unsigned short *l1, *l2;
   unsigned char *kc;
@@ -94,15 +94,17 @@ __device__ __forceinline__ FkSmem fk_carve(double *smem, int ntile)
   s.q = s.r + npad;                         // [n2] rqm / freep(k) of the points of list 2
   s.red = s.q + npad;                       // [FK_WARPS][FK_NKC][64] partial sums of the transfer coefficients
   s.vt = s.red + FK_WARPS * FK_NKC * 64;    // [FK_WARPS][FK_NKC]
-  s.l1 = (unsigned short *)(s.vt + FK_WARPS * FK_NKC);   // points with ff != 0 (sedimentation sums)
+  s.sc = s.vt + FK_WARPS * FK_NKC;          // [2][16] layer scalars: cm[4], cw[4], freep, t, p (double-buffered)
+  s.l1 = (unsigned short *)(s.sc + 32);     // points with ff != 0 (sedimentation sums)
   s.l2 = s.l1 + lpad;                       // ... whose bin has chemistry (transfer coefficients)
   s.kc = (unsigned char *)(s.l2 + lpad);    // [ntile] bin of the point, 255 = none
-  s.cnt = (int *)(s.kc + lpad);             // [2][FK_WARPS] list lengths per warp
+  s.cnt = (int *)(s.kc + lpad);             // [FK_WARPS] list lengths per warp (two 16-bit counts)
   return s;
 }
 
-__device__ __forceinline__ void fk_fetch(double *dst, const double *gf, int ntile)
+__device__ __forceinline__ void fk_fetch(double *dst, double *sc, const mistra_fastkmt_args &a, long long c, int ntile)
 {
+  const double *gf = a.ff + (size_t)c * ntile;
   if ((ntile & 1) == 0) {
     for (int q = threadIdx.x; q < (ntile >> 1); q += FK_THREADS)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst + 2 * q)),
@@ -112,6 +114,17 @@ __device__ __forceinline__ void fk_fetch(double *dst, const double *gf, int ntil
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst + q)),
                    "l"(gf + q) : "memory");
   }
+  // the layer's scalars travel with the tile: cm[0..3], cw[0..3], freep, t, p
+  const int tq = threadIdx.x;
+  const double *src = nullptr;
+  if (tq < 4) { if (tq < a.nkc) src = a.cm + c * a.nkc + tq; }
+  else if (tq < 8) { if (tq - 4 < a.nkc) src = a.cw + c * a.nkc + (tq - 4); }
+  else if (tq == 8) src = a.freep + c;
+  else if (tq == 9) src = a.t + c;
+  else if (tq == 10) src = a.p + c;
+  if (src)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(sc + tq)), "l"(src)
+                 : "memory");
   asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
 
@@ -124,7 +137,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fastkmt_kernel(long long ncell,
   const double z4pi3 = 4.0 * 3.1415926535897932 / 3.0;   // kpp.f90:2758
   const int nx = a.nx, nspec = a.nspec, nkc = a.nkc;
 
-  if ((long long)blockIdx.x < ncell) fk_fetch(s.f0, a.ff + (size_t)blockIdx.x * ntile, ntile);
+  if ((long long)blockIdx.x < ncell) fk_fetch(s.f0, s.sc, a, blockIdx.x, ntile);
   for (int q = threadIdx.x; q < ntile; q += FK_THREADS) {
     const int ia = q / nkt, jt = q - ia * nkt;
     s.r[q] = a.rq[q] * 1.e-6;
@@ -139,33 +152,57 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fastkmt_kernel(long long ncell,
   for (long long c = blockIdx.x; c < ncell; c += gridDim.x, buf ^= 1) {
     __syncthreads();                         // the other buffer, the lists and the partial sums are free again
     const long long cn = c + gridDim.x;
-    if (cn < ncell) fk_fetch(s.f0 + (buf ^ 1) * s.npad, a.ff + (size_t)cn * ntile, ntile);
-    // layer scalars while the tile is in flight
-    const double freep = a.freep[c], tk = a.t[c], pk = a.p[c];
-    unsigned onmask = 0;                     // bins with chemistry (cm > 0, kpp.f90:2826)
-    for (int kc = 0; kc < a.nkc_l; ++kc)
-      if (a.cm[c * nkc + kc] > 0.0) onmask |= 1u << kc;
-    double vm0 = 1.0, vm1 = 1.0, x10 = 1.0, x11 = 1.0;     // idle lanes: 1 / (q + 1), never stored (a zero
-                                                           // numerator would send the whole warp down the slow path of the division)
-    if (sp0 >= 0) {
-      const double al = a.alpha[c * nspec + sp0];
-      vm0 = a.vmean[c * nspec + sp0];
-      x10 = (al > 0.0) ? 4. / (3. * al) : 0.0;             // kpp.f90:2890
-    }
-    if (sp1 >= 0) {
-      const double al = a.alpha[c * nspec + sp1];
-      vm1 = a.vmean[c * nspec + sp1];
-      x11 = (al > 0.0) ? 4. / (3. * al) : 0.0;
-    }
+    if (cn < ncell) fk_fetch(s.f0 + (buf ^ 1) * s.npad, s.sc + (buf ^ 1) * 16, a, cn, ntile);
+    // the species' accommodation coefficient and mean speed while the tile is in flight
+    // (loads issued here, consumed in step 3).  Idle lanes: 1 / (q + 1), never stored - a zero numerator
+    // would send the whole warp down the slow path of the division.
+    double vm0 = 1.0, vm1 = 1.0, al0 = 0.75, al1 = 0.75;
+    if (sp0 >= 0) { al0 = a.alpha[c * nspec + sp0]; vm0 = a.vmean[c * nspec + sp0]; }
+    if (sp1 >= 0) { al1 = a.alpha[c * nspec + sp1]; vm1 = a.vmean[c * nspec + sp1]; }
     if (cn < ncell) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     else            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
-    const double *sf = s.f0 + buf * s.npad;
+    const double *sf = s.f0 + buf * s.npad, *sc = s.sc + buf * 16;
+    const double freep = sc[8], tk = sc[9], pk = sc[10];
+    unsigned onmask = 0;                     // bins with chemistry (cm > 0, kpp.f90:2826)
+    for (int kc = 0; kc < a.nkc_l; ++kc)
+      if (sc[kc] > 0.0) onmask |= 1u << kc;
 
-    // (1) compaction in grid order
-    int n1 = 0, n2 = 0;
-    for (int base = 0; base < ntile; base += FK_THREADS) {
-      const int q = base + threadIdx.x;
+    // (1) compaction in grid order: warp w owns the contiguous segment [w * seg, (w + 1) * seg) of the grid;
+    // first pass counts, one exclusive scan over the warps, second pass writes the indices
+    const int seg = ((ntile + FK_WARPS - 1) / FK_WARPS + 31) & ~31;
+    const int q0 = warp * seg;
+    const unsigned below = (1u << lane) - 1u;
+    int c1 = 0, c2 = 0;
+    for (int base = q0; base < q0 + seg; base += 32) {
+      const int q = base + lane;
+      bool act1 = false, act2 = false;
+      if (q < ntile) {
+        const int kc = s.kc[q];
+        act1 = kc != 255 && sf[q] != 0.0;
+        act2 = act1 && ((onmask >> kc) & 1u);
+      }
+      c1 += __popc(__ballot_sync(0xffffffffu, act1));
+      c2 += __popc(__ballot_sync(0xffffffffu, act2));
+    }
+    if (lane == 0) s.cnt[warp] = c1 | (c2 << 16);
+    __syncthreads();
+    int n1, n2, o1, o2;
+    {
+      const int mine = lane < FK_WARPS ? s.cnt[lane] : 0;   // both counts < 2^16
+      int inc = mine;
+#pragma unroll
+      for (int off = 1; off < FK_WARPS; off <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += up;
+      }
+      const int tot = __shfl_sync(0xffffffffu, inc, FK_WARPS - 1);
+      const int exc = __shfl_sync(0xffffffffu, inc - mine, warp);
+      n1 = tot & 0xffff; n2 = tot >> 16;
+      o1 = exc & 0xffff; o2 = exc >> 16;
+    }
+    for (int base = q0; base < q0 + seg; base += 32) {
+      const int q = base + lane;
       bool act1 = false, act2 = false;
       if (q < ntile) {
         const int kc = s.kc[q];
@@ -173,20 +210,11 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fastkmt_kernel(long long ncell,
         act2 = act1 && ((onmask >> kc) & 1u);
       }
       const unsigned b1 = __ballot_sync(0xffffffffu, act1), b2 = __ballot_sync(0xffffffffu, act2);
-      if (lane == 0) { s.cnt[warp] = __popc(b1); s.cnt[FK_WARPS + warp] = __popc(b2); }
-      __syncthreads();
-      int o1 = n1, o2 = n2;
-#pragma unroll
-      for (int w = 0; w < FK_WARPS; ++w) {
-        const int c1 = s.cnt[w], c2 = s.cnt[FK_WARPS + w];
-        if (w < warp) { o1 += c1; o2 += c2; }
-        n1 += c1; n2 += c2;
-      }
-      const unsigned below = (1u << lane) - 1u;
       if (act1) s.l1[o1 + __popc(b1 & below)] = (unsigned short)q;
       if (act2) s.l2[o2 + __popc(b2 & below)] = (unsigned short)q;
-      __syncthreads();
+      o1 += __popc(b1); o2 += __popc(b2);
     }
+    __syncthreads();
 
     // (2) q = rqm / freep of list 2; sedimentation sums over list 1 (kpp.f90:2924-2927)
     for (int i = threadIdx.x; i < n2; i += FK_THREADS) s.q[i] = s.r[s.l2[i]] / freep;
@@ -207,6 +235,8 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fastkmt_kernel(long long ncell,
 
     // (3) transfer coefficients (kpp.f90:2913-2922); warp-uniform control flow
     if (n2 > 0) {
+      const double x10 = (al0 > 0.0) ? 4. / (3. * al0) : 0.0;   // kpp.f90:2890
+      const double x11 = (al1 > 0.0) ? 4. / (3. * al1) : 0.0;
       double a00 = 0.0, a01 = 0.0, a02 = 0.0, a03 = 0.0, a10 = 0.0, a11 = 0.0, a12 = 0.0, a13 = 0.0;
       for (int i = warp; i < n2; i += 3 * FK_WARPS) {
         const int ib = i + FK_WARPS, ic = i + 2 * FK_WARPS;
@@ -236,7 +266,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fastkmt_kernel(long long ncell,
     if (threadIdx.x < FK_NKC * 64) {
       const int kc = threadIdx.x >> 6, l = threadIdx.x & 63;
       if (kc < a.nkc_l && l < nx && ((onmask >> kc) & 1u)) {
-        const double cw = a.cw[c * nkc + kc];
+        const double cw = sc[4 + kc];
         if (cw > 0.0) {
           double sum = 0.0;
           if (n2 > 0)
@@ -247,7 +277,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fastkmt_kernel(long long ncell,
     } else if (threadIdx.x < FK_NKC * 64 + FK_NKC) {
       const int kc = threadIdx.x - FK_NKC * 64;
       if (kc < a.nkc_l) {
-        const double cw = a.cw[c * nkc + kc];
+        const double cw = sc[4 + kc];
         if (cw > 0.0) {
           double sum = 0.0;
           for (int w = 0; w < FK_WARPS; ++w) sum = sum + s.vt[w * 4 + kc];
@@ -295,7 +325,7 @@ int check(int64_t ncell, const mistra_fastkmt_args *a)
 size_t smem_bytes(const mistra_fastkmt_args *a)
 {
   const size_t ntile = (size_t)a->nka * a->nkt, npad = (ntile + 1) & ~(size_t)1, lpad = (ntile + 7) & ~(size_t)7;
-  return sizeof(double) * (4 * npad + FK_WARPS * FK_NKC * 64 + FK_WARPS * FK_NKC) + 2 * 2 * lpad + lpad +
+  return sizeof(double) * (4 * npad + FK_WARPS * FK_NKC * 64 + FK_WARPS * FK_NKC + 32) + 2 * 2 * lpad + lpad +
          sizeof(int) * 2 * FK_WARPS;
 }
 

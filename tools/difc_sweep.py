@@ -36,6 +36,12 @@ def timeit(fn, reps=5):
 m1 = timeit(lambda: dm.difc_device(60.0, dd["atkh"], dd["w"], dd["am3"], dd["detw"], dd["deta"], fd))
 m2 = timeit(lambda: dm.difp_device(60.0, dd["atkh"][:500], dd["w"][:500], rho, dd["detw"], dd["deta"], ffp, fsp))
 b1 = ncol * 821 * (2 * (n - 2) + 1) * 8
-b2 = 500 * 4900 * 3 * (n - 1) * 8
+b2 = 500 * 4900 * 2 * (n - 1) * 8
+ffp.mul_((torch.rand_like(ffp) < 0.05).double())          # 5 % of the bins populated, as real spectra are
+for a, _ in fd:
+    a[:, :, ::3] = 0.0                                     # species absent from the column
+m3 = timeit(lambda: dm.difc_device(60.0, dd["atkh"], dd["w"], dd["am3"], dd["detw"], dd["deta"], fd))
+m4 = timeit(lambda: dm.difp_device(60.0, dd["atkh"][:500], dd["w"][:500], rho, dd["detw"], dd["deta"], ffp, fsp))
+print("sparse inputs: difc %.3f ms  difp %.3f ms" % (m3, m4))
 print("CTAs/SM %s: difc %.3f ms (%.0f GB/s)  difp %.3f ms (%.0f GB/s)" % (
     os.environ.get("MISTRA_DIFC_CTAS_PER_SM", "16"), m1, b1 / m1 * 1e-6, m2, b2 / m2 * 1e-6))
