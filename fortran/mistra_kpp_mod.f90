@@ -230,3 +230,34 @@ module mistra_difc_mod
      end function mistra_difc
   end interface
 end module mistra_difc_mod
+
+! mistra_drive_mod - ISO_C_BINDING interface of include/mistra_drive.h: the gather / scatter halves of
+! gas_drive / aer_drive / tot_drive (aer.f:146-178, 233-245) for a batch of layers on device-resident arrays.
+module mistra_drive_mod
+  use, intrinsic :: iso_c_binding
+  implicit none
+  type, bind(C) :: mistra_drive_args
+     integer(c_int32_t) :: nvar, nfix, j1, j5, j2, j6, nkc, nmap
+     type(c_ptr) :: map_kpp, map_arr, map_off, layer, s1, s3, sl1, sion1, var, fix
+     integer(c_int32_t) :: clamp_liquid, f32_literals, indf_o2, indf_h2o, indf_n2
+     integer(c_int32_t) :: indf_h2ol(4)
+     type(c_ptr) :: air, h2o, cvv
+     integer(c_int32_t) :: clip_negative
+  end type mistra_drive_args
+  interface
+     function mistra_drive_gather_device(ncell, a, stream) result(rc) bind(C, name="mistra_drive_gather_device")
+       import :: c_int, c_int64_t, c_ptr, mistra_drive_args
+       integer(c_int64_t), value :: ncell
+       type(mistra_drive_args), intent(in) :: a
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_drive_gather_device
+     function mistra_drive_scatter_device(ncell, a, stream) result(rc) bind(C, name="mistra_drive_scatter_device")
+       import :: c_int, c_int64_t, c_ptr, mistra_drive_args
+       integer(c_int64_t), value :: ncell
+       type(mistra_drive_args), intent(in) :: a
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_drive_scatter_device
+  end interface
+end module mistra_drive_mod

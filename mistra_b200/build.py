@@ -29,9 +29,9 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", HOSTCXX]
 
 UNITS = ["kpp_mech_g.cu", "kpp_mech_a.cu", "kpp_mech_t.cu", "kpp_api.cu", "bins_kernels.cu",
-         "kon_kernels.cu", "konc_kernels.cu", "cwrc_kernels.cu", "fastkmt_kernels.cu", "difc_kernels.cu", "rconst_kernels.cu", "_gen/kpp_names.cpp"]
+         "kon_kernels.cu", "konc_kernels.cu", "cwrc_kernels.cu", "fastkmt_kernels.cu", "difc_kernels.cu", "drive_kernels.cu", "rconst_kernels.cu", "_gen/kpp_names.cpp"]
 # per-unit flags: the condensation kernel keeps the reference's unfused arithmetic
-UNIT_FLAGS = {"kon_kernels.cu": ["-fmad=false"], "konc_kernels.cu": ["-fmad=false"], "cwrc_kernels.cu": ["-fmad=false"], "fastkmt_kernels.cu": ["-fmad=false"], "difc_kernels.cu": ["-fmad=false"],
+UNIT_FLAGS = {"kon_kernels.cu": ["-fmad=false"], "konc_kernels.cu": ["-fmad=false"], "cwrc_kernels.cu": ["-fmad=false"], "fastkmt_kernels.cu": ["-fmad=false"], "difc_kernels.cu": ["-fmad=false"], "drive_kernels.cu": ["-fmad=false"],
               "rconst_kernels.cu": ["-fmad=false"]}
 
 
@@ -59,6 +59,8 @@ def _deps(unit):
         deps.append(os.path.join(ROOT, "include", "mistra_fastkmt.h"))
     if unit.startswith("difc_"):
         deps.append(os.path.join(ROOT, "include", "mistra_difc.h"))
+    if unit.startswith("drive_"):
+        deps.append(os.path.join(ROOT, "include", "mistra_drive.h"))
     if unit.startswith("rconst_"):
         deps += [os.path.join(ROOT, "include", "mistra_rconst.h"), os.path.join(ROOT, "include", "mistra_rconst_cuda.h"),
                  os.path.join(CSRC, "rate_laws.h"), os.path.join(CSRC, "rconst_common.h")]

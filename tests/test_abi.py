@@ -27,6 +27,7 @@ def declared_functions(header):
                                         ("mistra_cwrc.h", "libmistra_kpp.so"),
                                         ("mistra_fastkmt.h", "libmistra_kpp.so"),
                                         ("mistra_difc.h", "libmistra_kpp.so"),
+                                        ("mistra_drive.h", "libmistra_kpp.so"),
                                         ("mistra_rconst_cuda.h", "libmistra_kpp.so"),
                                         ("mistra_rconst.h", "libmistra_rconst.so")])
 def test_library_exports_every_declared_symbol(kpp, header, lib):
