@@ -812,6 +812,36 @@ def run_next_rows_leg(args, dev, world, rank, barrier):
                                        "sample": "%d x %d columns, OpenMP over columns (includes a copy of the arrays), "
                                                  "%.1f s" % (reps, m, dt)}
     del dd, ffp, fsp, rho
+    # ---- gather / scatter halves of aer_drive on device-resident model arrays (rows a14 / a15) ----
+    from mistra_b200 import drive
+    from mistra_b200.mechgen import mech as mechmod
+    ma = mechmod.load("aer")
+    gasph = [x for x in ma.spc_names[:ma.nvar] if x[-2:] not in ("l1", "l2")]
+    mp = drive.to_device(drive.drive_map("aer", gasph[:75], gasph[75:95]), dev)
+    ncd = max(1, args.cols // 10) * 98                            # the aer cells of the rconst leg
+    rr = np.random.default_rng(20261018 + rank)
+    lay = torch.from_numpy(rr.permutation(ncd).astype(np.int64)).to(dev)
+    marr = [torch.rand(sh, dtype=torch.float64, device=dev) for sh in ((ncd, 75), (ncd, 20), (ncd, 4, 121), (ncd, 4, 55))]
+    vard = torch.zeros((ncd, ma.nvar), dtype=torch.float64, device=dev)
+    fixd = torch.zeros((ncd, ma.nfix), dtype=torch.float64, device=dev)
+    aird, h2od, cvvd = (torch.rand(sh, dtype=torch.float64, device=dev) + 0.5 for sh in ((ncd,), (ncd,), (ncd, 4)))
+    l0 = drive.launch_count()
+
+    def drive_step():
+        drive.gather_device(mp, lay, *marr, aird, h2od, cvvd, vard, fixd)
+        drive.scatter_device(mp, lay, *marr, vard, fixd)
+    ms = timeit(drive_step)
+    nm = int(mp["kpp_d"].numel())
+    by = ncd * ((2 * nm + 7) * 8 * 2 + 4 * (121 + 55) * 16 * 2 + (75 + 20) * 16)
+    res["drive"] = {"metric": "drive_gather_scatter_cells_per_s", "value": ncd * world / (ms * 1e-3), "unit": "cells/s",
+                    "mechanism": "aer", "cells_per_gpu": ncd, "ms_per_step": ms, "gpu_launches": int(drive.launch_count() - l0),
+                    "roofline": {"bound": "hbm", "kernel": "drive_gather_kernel + drive_scatter_kernel",
+                                 "achieved": by / (ms * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": by / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"], "peak_source": peak_src, "traffic": None,
+                                 "note": "per cell: %d copies each way (read + write), the clamp of the liquid rows (4*176 "
+                                         "doubles read + written) before and the clip of all four rows after; layers in "
+                                         "random order" % nm}}
+    del marr, vard, fixd, lay
     # ---- Update_RCONST_a ----
     ens = synthetic.AerEnsemble(max(1, args.cols // 10), seed=20261018 + rank)
     tn = lambda a: None if a is None else t(a)

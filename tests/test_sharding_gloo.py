@@ -61,3 +61,36 @@ def test_two_rank_gloo_run_equals_single_process(tmp_path, oracle):
     want = shard.diagnostics_vector(ierr, stats)
     for p in parts:
         assert np.array_equal(p["diag"], want)
+
+
+def _worker_columns(rank, world, port, total_cols, outdir):
+    """The column-wise operators (difc on the chemistry arrays, drive copies) shard the same way: whole columns
+    per rank, nothing exchanged."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from mistra_b200 import shard
+    from oracle import difc_oracle as dfo
+    from tests.test_difc_oracle import inputs, run
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    first, n = shard.column_block(total_cols, world, rank)
+    c, fields = inputs(total_cols, 17, n=40, sizes=(9, 4, 3 * 4, 2 * 4))      # every rank builds the same ensemble
+    mine = {k: (v[first:first + n] if v.ndim == 2 else v) for k, v in c.items()}
+    outs = run(dfo.difc, 60.0, mine, [(a[first:first + n], p) for a, p in fields])
+    np.savez(os.path.join(outdir, "cols%d.npz" % rank), first=first, n=n, **{"o%d" % i: o for i, o in enumerate(outs)})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_column_operators_equal_single_process(tmp_path):
+    from oracle import difc_oracle as dfo
+    from tests.test_difc_oracle import inputs, run
+    total_cols, world = 7, 2
+    mp.spawn(_worker_columns, args=(world, _free_port(), total_cols, str(tmp_path)), nprocs=world, join=True)
+    c, fields = inputs(total_cols, 17, n=40, sizes=(9, 4, 3 * 4, 2 * 4))
+    ref = run(dfo.difc, 60.0, c, fields)
+    parts = [np.load(os.path.join(str(tmp_path), "cols%d.npz" % r)) for r in range(world)]
+    assert [int(p["n"]) for p in parts] == [4, 3]
+    for i, r in enumerate(ref):
+        assert np.array_equal(np.concatenate([p["o%d" % i] for p in parts]), r)
