@@ -42,8 +42,9 @@ def test_device_resident_chain(cuda_device, kpp):
     gd = {"nka": g["nka"], "nkt": g["nkt"], "ka": g["ka"], "kw": t(g["kw"], np.int32), "e": t(g["e"]), "rq": t(g["rq"])}
     outs = [torch.empty((n, 4), dtype=torch.float64, device=cuda_device) for _ in range(4)]
     xk, vt = t(xk0), t(vt0)
-    sap, smp = (torch.empty((n, 4), dtype=torch.float64, device=cuda_device) for _ in range(2))
-    so = torch.empty((n, 4, 9), dtype=torch.float64, device=cuda_device)
+    # the snapshot assigns sion1o only for bins with chemistry (str.f90:5950-5960); start from zeros like the host form
+    sap, smp = (torch.zeros((n, 4), dtype=torch.float64, device=cuda_device) for _ in range(2))
+    so = torch.zeros((n, 4, 9), dtype=torch.float64, device=cuda_device)
     feu_d, cloud_d, lex_d, fr_d, al_d, vm_d, si_d = (t(d["feualt"]), t(cloud, np.int32), t(lex, np.int32), t(freep),
                                                       t(alpha), t(vmean), t(sion1))
     torch.cuda.synchronize()
