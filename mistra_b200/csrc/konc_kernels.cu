@@ -55,24 +55,28 @@ __global__ void __launch_bounds__(KONC_THREADS) konc_kernel(long long ncell, mis
       if (delta < 0.0) { atomicAdd(&s_warn[1], 1); delta = 0.0; }
       else if (delta > 1.0) { atomicAdd(&s_warn[2], 1); delta = 0.0; }
       s_delta[ia] = delta;
-      s_dir[ia] = from_a ? 1 : -1;
+      s_dir[ia] = (delta > 0.0) ? (from_a ? 1 : -1) : 0;     // 0: class leaves the species unchanged
     }
     __syncthreads();
     for (int l = threadIdx.x; l < nsp; l += blockDim.x) {
       double *base = (l < j2) ? a.sl1 + (c * 4) * j2 + l : a.sion1 + (c * 4) * j6 + (l - j2);
       const int stride = (l < j2) ? j2 : j6;
       double s0 = base[0], s1 = base[stride], s2 = base[2 * stride], s3 = base[3 * stride];
-      for (int ia = 0; ia < nka; ++ia) {
+      // small classes exchange between bins 1 <-> 3, large ones between 2 <-> 4 (two loops, integer tests only)
+      const int kas = ka < nka ? ka : nka;
+      for (int ia = 0; ia < kas; ++ia) {
+        const int dir = s_dir[ia];
+        if (dir == 0) continue;
         const double delta = s_delta[ia];
-        if (!(delta > 0.0)) continue;
-        const bool from_a = s_dir[ia] > 0;
-        if (ia < ka) {       // bins 1 <-> 3
-          if (from_a) { const double del = s0 * delta; s0 = fmax(0.0, s0 - del); s2 = fmax(0.0, s2 + del); }
-          else        { const double del = s2 * delta; s2 = fmax(0.0, s2 - del); s0 = fmax(0.0, s0 + del); }
-        } else {             // bins 2 <-> 4
-          if (from_a) { const double del = s1 * delta; s1 = fmax(0.0, s1 - del); s3 = fmax(0.0, s3 + del); }
-          else        { const double del = s3 * delta; s3 = fmax(0.0, s3 - del); s1 = fmax(0.0, s1 + del); }
-        }
+        if (dir > 0) { const double del = s0 * delta; s0 = fmax(0.0, s0 - del); s2 = fmax(0.0, s2 + del); }
+        else         { const double del = s2 * delta; s2 = fmax(0.0, s2 - del); s0 = fmax(0.0, s0 + del); }
+      }
+      for (int ia = kas; ia < nka; ++ia) {
+        const int dir = s_dir[ia];
+        if (dir == 0) continue;
+        const double delta = s_delta[ia];
+        if (dir > 0) { const double del = s1 * delta; s1 = fmax(0.0, s1 - del); s3 = fmax(0.0, s3 + del); }
+        else         { const double del = s3 * delta; s3 = fmax(0.0, s3 - del); s1 = fmax(0.0, s1 + del); }
       }
       if (a.pntot[c * 4 + 2] < 1.e-7) { s0 = s0 + fmax(0.0, s2); s2 = 0.0; }
       if (a.pntot[c * 4 + 3] < 1.e-7) { s1 = s1 + fmax(0.0, s3); s3 = 0.0; }
