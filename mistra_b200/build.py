@@ -29,7 +29,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", HOSTCXX]
 
 UNITS = ["kpp_mech_g.cu", "kpp_mech_a.cu", "kpp_mech_t.cu", "kpp_api.cu", "bins_kernels.cu",
-         "kon_kernels.cu", "konc_kernels.cu", "cwrc_kernels.cu", "fastkmt_kernels.cu", "difc_kernels.cu", "drive_kernels.cu", "rconst_kernels.cu", "_gen/kpp_names.cpp"]
+         "kon_kernels.cu", "konc_kernels.cu", "cwrc_kernels.cu", "fastkmt_kernels.cu", "difc_kernels.cu", "drive_kernels.cu", "rconst_kernels.cu", "_gen/kpp_names.cpp",
+         "_gen/onchip_tables_g_%(v)s.cpp", "_gen/onchip_tables_a_%(v)s.cpp"]
 # per-unit flags: the condensation kernel keeps the reference's unfused arithmetic
 UNIT_FLAGS = {"kon_kernels.cu": ["-fmad=false"], "konc_kernels.cu": ["-fmad=false"], "cwrc_kernels.cu": ["-fmad=false"], "fastkmt_kernels.cu": ["-fmad=false"], "difc_kernels.cu": ["-fmad=false"], "drive_kernels.cu": ["-fmad=false"],
               "rconst_kernels.cu": ["-fmad=false"]}
@@ -68,6 +69,8 @@ def _deps(unit):
     if unit.startswith("kpp_mech_"):
         x = unit[len("kpp_mech_")]
         deps += [os.path.join(CSRC, "_gen", "mech_%s.cuh" % x), os.path.join(CSRC, "ros3_kernel.inc")]
+        if x in "ga":
+            deps += [os.path.join(CSRC, "_gen", "onchip_%s.cuh" % x), os.path.join(CSRC, "ros3_onchip.inc")]
     return deps
 
 
@@ -95,6 +98,8 @@ def _compile(unit, flags, tag, verbose):
 def build(verbose=False, strict=True, ptxas_v=False):
     subprocess.check_call([sys.executable, "-m", "mistra_b200.mechgen.emit_cuda"], cwd=ROOT,
                           stdout=subprocess.DEVNULL)
+    subprocess.check_call([sys.executable, "-m", "mistra_b200.mechgen.onchip"], cwd=ROOT,
+                          stdout=subprocess.DEVNULL)
     variants = [("fast", [], "libmistra_kpp.so")]
     if strict:
         variants.append(("strict", ["-DKPP_STRICT", "-fmad=false"], "libmistra_kpp_strict.so"))
@@ -103,7 +108,7 @@ def build(verbose=False, strict=True, ptxas_v=False):
         for tag, flags, _ in variants:
             fl = flags + (["-Xptxas", "-v"] if ptxas_v else [])
             for u in UNITS:
-                jobs.append((tag, ex.submit(_compile, u, fl, tag, verbose)))
+                jobs.append((tag, ex.submit(_compile, u % {"v": tag}, fl, tag, verbose)))
         objs = {}
         for tag, j in jobs:
             objs.setdefault(tag, []).append(j.result())
@@ -128,7 +133,7 @@ def build_variant(tag, extra_flags, units=("kpp_mech_a.cu",), verbose=False):
     MISTRA_KPP_LIB=libmistra_kpp_<tag>.so (mistra_b200/kpp.py)."""
     objs = []
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
-        jobs = [ex.submit(_compile, u, list(extra_flags) if u in units else [], tag if u in units else "fast", verbose)
+        jobs = [ex.submit(_compile, u % {"v": "fast"}, list(extra_flags) if u in units else [], tag if u in units else "fast", verbose)
                 for u in UNITS]
         objs = [j.result() for j in jobs]
     so = os.path.join(HERE, "libmistra_kpp_%s.so" % tag)

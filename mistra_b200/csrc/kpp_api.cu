@@ -25,6 +25,8 @@ struct MechState {
   size_t ws_bytes = 0;
   int blocks = 0;
   int coef_variant = -1;  // -1 unset, 0 f64 literals, 1 f32 literals
+  bool onchip = false;    // one thread block per cell (ros3_onchip.inc) instead of one thread per cell
+  unsigned short *oc_tab = nullptr;   // device copy of the on-chip kernel's instruction streams
 };
 
 struct DeviceState {
@@ -150,27 +152,61 @@ double literal_value(const char *lit, int f32)
   return f32 ? (double)strtof(lit, nullptr) : strtod(lit, nullptr);
 }
 
+// MISTRA_KPP_ONCHIP=0 selects the round-1 mapping (one cell per thread, workspace in HBM) where an
+// on-chip kernel exists - for A/B measurements only; both are CUDA paths, there is no CPU path.
+bool want_onchip(const KppMechInfo *mi)
+{
+  if (!mi->oc_kernel) return false;
+  const char *e = getenv("MISTRA_KPP_ONCHIP");
+  return !(e && atoi(e) == 0);
+}
+
 int ensure_mech(DeviceState &d, int mech, const KppMechInfo *mi, int f32, cudaStream_t st)
 {
   MechState &ms = d.mech[mech];
-  if (!ms.ws) {
+  if (!ms.ws && !ms.oc_tab) {
+    ms.onchip = want_onchip(mi);
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mi->kernel, KPP_BLOCK, 0));
+    if (ms.onchip) {
+      CK(cudaFuncSetAttribute(mi->oc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mi->oc_smem_bytes));
+      CK(cudaFuncSetAttribute(mi->oc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mi->oc_kernel, mi->oc_threads, mi->oc_smem_bytes));
+    } else {
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mi->kernel, KPP_BLOCK, 0));
+    }
     if (per_sm < 1) return fail(MISTRA_KPP_ECUDA, "kernel does not fit on an SM");
     if (const char *e = getenv("MISTRA_KPP_BLOCKS_PER_SM")) {
       int v = atoi(e);
       if (v >= 1 && v < per_sm) per_sm = v;
     }
     ms.blocks = per_sm * d.num_sm;
-    const size_t warps = (size_t)ms.blocks * (KPP_BLOCK / 32);
-    ms.ws_bytes = warps * (size_t)mi->nslot * 32 * sizeof(double);
-    CK(cudaMalloc(&ms.ws, ms.ws_bytes));
+    if (ms.onchip) {
+      CK(cudaMalloc(&ms.oc_tab, mi->oc_table_count * sizeof(unsigned short)));
+      CK(cudaMemcpyAsync(ms.oc_tab, mi->oc_tables, mi->oc_table_count * sizeof(unsigned short),
+                         cudaMemcpyHostToDevice, st));
+#ifdef KPP_STRICT
+      // strict build: the tail block of the LU factors is also written out, for the reference-order
+      // backward substitution
+      ms.ws_bytes = (size_t)ms.blocks * mi->oc_tail * mi->oc_tail * sizeof(double);
+      CK(cudaMalloc(&ms.ws, ms.ws_bytes));
+#endif
+    } else {
+      const size_t warps = (size_t)ms.blocks * (KPP_BLOCK / 32);
+      ms.ws_bytes = warps * (size_t)mi->nslot * 32 * sizeof(double);
+      CK(cudaMalloc(&ms.ws, ms.ws_bytes));
+    }
   }
   if (ms.coef_variant != f32) {
     double h[64];
-    if (mi->ncoef > 64) return fail(MISTRA_KPP_EINVAL, "coefficient table too large");
-    for (int i = 0; i < mi->ncoef; ++i) h[i] = literal_value(mi->coef_literals[i], f32);
-    CK(mi->set_coef(h, st));
+    if (ms.onchip) {
+      if (mi->oc_nlit > 64) return fail(MISTRA_KPP_EINVAL, "coefficient table too large");
+      for (int i = 0; i < mi->oc_nlit; ++i) h[i] = literal_value(mi->oc_literals[i], f32);
+      CK(mi->oc_set_lit(h, st));
+    } else {
+      if (mi->ncoef > 64) return fail(MISTRA_KPP_EINVAL, "coefficient table too large");
+      for (int i = 0; i < mi->ncoef; ++i) h[i] = literal_value(mi->coef_literals[i], f32);
+      CK(mi->set_coef(h, st));
+    }
     CK(cudaStreamSynchronize(st));  // h is on the stack
     ms.coef_variant = f32;
   }
@@ -199,14 +235,20 @@ int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rcons
   b.hexit = d_hexit;
   b.texit = d_texit;
   b.ncell = ncell;
-  if (slot == 1 && !ms.ws2) CK(cudaMalloc(&ms.ws2, ms.ws_bytes));
+  if (slot == 1 && !ms.ws2 && ms.ws_bytes) CK(cudaMalloc(&ms.ws2, ms.ws_bytes));
   b.ws = slot ? ms.ws2 : ms.ws;
+  b.oc_tab = ms.oc_tab;
   b.counter = d.counter + slot;
   CK(cudaStreamWaitEvent(st, d.ev_slot[slot], 0));
   CK(cudaMemsetAsync(b.counter, 0, sizeof(unsigned long long), st));
-  long long need_blocks = (ncell + KPP_BLOCK - 1) / KPP_BLOCK;
-  int blocks = (int)(need_blocks < ms.blocks ? need_blocks : ms.blocks);
-  CK(mi->launch(b, blocks, st));
+  if (ms.onchip) {
+    int blocks = (int)(ncell < ms.blocks ? ncell : ms.blocks);
+    CK(mi->oc_launch(b, blocks, st));
+  } else {
+    long long need_blocks = (ncell + KPP_BLOCK - 1) / KPP_BLOCK;
+    int blocks = (int)(need_blocks < ms.blocks ? need_blocks : ms.blocks);
+    CK(mi->launch(b, blocks, st));
+  }
   CK(cudaEventRecord(d.ev_slot[slot], st));
   g_launches.fetch_add(1);
   return 0;
@@ -314,7 +356,7 @@ int mistra_kpp_integrate_device(int mech, int64_t ncell, const double *d_rconst,
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream, as in the CUDA runtime
   // Experiment (MISTRA_KPP_SPLIT=1): the two halves of a long batch as two co-resident kernels.
   static const bool split = getenv("MISTRA_KPP_SPLIT") && atoi(getenv("MISTRA_KPP_SPLIT")) > 0;
-  if (split && ncell >= 8LL * d->num_sm * 2 * KPP_BLOCK) {
+  if (split && !want_onchip(mech_info(mech)) && ncell >= 8LL * d->num_sm * 2 * KPP_BLOCK) {
     const KppMechInfo *mi = mech_info(mech);
     if ((rc = ensure_streams(d))) return rc;
     const int64_t h = ncell / 2;
@@ -385,7 +427,7 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
   // Host buffers may be pageable (Fortran arrays) or pinned; cudaMemcpyAsync handles
   // both, only pinned ones actually overlap.
   if ((rc = ensure_mech(*d, mech, mi, o ? (o->f32_literals ? 1 : 0) : 1, st))) return rc;
-  const int64_t resident = (int64_t)d->mech[mech].blocks * KPP_BLOCK;
+  const int64_t resident = (int64_t)d->mech[mech].blocks * (d->mech[mech].onchip ? 8 : KPP_BLOCK);
   int64_t nchunk = ncell / (2 * resident);
   if (nchunk < 1) nchunk = 1;
   if (nchunk > 16) nchunk = 16;
@@ -453,6 +495,7 @@ int mistra_kpp_finalize(void)
     for (auto &m : d.mech) {
       if (m.ws) cudaFree(m.ws);
       if (m.ws2) cudaFree(m.ws2);
+      if (m.oc_tab) cudaFree(m.oc_tab);
       m = MechState();
     }
     if (d.counter) cudaFree(d.counter);
