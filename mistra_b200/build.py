@@ -28,7 +28,7 @@ HOSTCXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", HOSTCXX]
 
-UNITS = ["kpp_mech_g.cu", "kpp_mech_a.cu", "kpp_mech_t.cu", "kpp_api.cu", "bins_kernels.cu",
+UNITS = ["kpp_mech_g.cu", "kpp_mech_a.cu", "kpp_mech_t.cu", "kpp_onchip_g.cu", "kpp_onchip_a.cu", "kpp_api.cu", "bins_kernels.cu",
          "kon_kernels.cu", "konc_kernels.cu", "cwrc_kernels.cu", "fastkmt_kernels.cu", "difc_kernels.cu", "drive_kernels.cu", "rconst_kernels.cu", "_gen/kpp_names.cpp",
          "_gen/onchip_tables_g_%(v)s.cpp", "_gen/onchip_tables_a_%(v)s.cpp"]
 # per-unit flags: the condensation kernel keeps the reference's unfused arithmetic
@@ -69,8 +69,12 @@ def _deps(unit):
     if unit.startswith("kpp_mech_"):
         x = unit[len("kpp_mech_")]
         deps += [os.path.join(CSRC, "_gen", "mech_%s.cuh" % x), os.path.join(CSRC, "ros3_kernel.inc")]
-        if x in "ga":
-            deps += [os.path.join(CSRC, "_gen", "onchip_%s.cuh" % x), os.path.join(CSRC, "ros3_onchip.inc")]
+    if unit.startswith("kpp_onchip_"):
+        x = unit[len("kpp_onchip_")]
+        deps += [os.path.join(CSRC, "_gen", "onchip_%s.cuh" % x), os.path.join(CSRC, "ros3_onchip.inc"),
+                 os.path.join(CSRC, "kpp_onchip.h")]
+    if unit == "kpp_api.cu":
+        deps.append(os.path.join(CSRC, "kpp_onchip.h"))
     return deps
 
 

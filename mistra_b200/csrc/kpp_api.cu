@@ -3,7 +3,7 @@
 // staging and kernel launches.  No CPU fallback: every compute entry needs a
 // CUDA device.
 #include "../../include/mistra_kpp.h"
-#include "kpp_batch.h"
+#include "kpp_onchip.h"
 
 #include <atomic>
 #include <cmath>
@@ -156,7 +156,7 @@ double literal_value(const char *lit, int f32)
 // on-chip kernel exists - for A/B measurements only; both are CUDA paths, there is no CPU path.
 bool want_onchip(const KppMechInfo *mi)
 {
-  if (!mi->oc_kernel) return false;
+  if (!mi->oc) return false;
   const char *e = getenv("MISTRA_KPP_ONCHIP");
   return !(e && atoi(e) == 0);
 }
@@ -168,9 +168,9 @@ int ensure_mech(DeviceState &d, int mech, const KppMechInfo *mi, int f32, cudaSt
     ms.onchip = want_onchip(mi);
     int per_sm = 0;
     if (ms.onchip) {
-      CK(cudaFuncSetAttribute(mi->oc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mi->oc_smem_bytes));
-      CK(cudaFuncSetAttribute(mi->oc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mi->oc_kernel, mi->oc_threads, mi->oc_smem_bytes));
+      CK(cudaFuncSetAttribute(mi->oc->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mi->oc->smem_bytes));
+      CK(cudaFuncSetAttribute(mi->oc->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mi->oc->kernel, mi->oc->threads, mi->oc->smem_bytes));
     } else {
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mi->kernel, KPP_BLOCK, 0));
     }
@@ -181,13 +181,13 @@ int ensure_mech(DeviceState &d, int mech, const KppMechInfo *mi, int f32, cudaSt
     }
     ms.blocks = per_sm * d.num_sm;
     if (ms.onchip) {
-      CK(cudaMalloc(&ms.oc_tab, mi->oc_table_count * sizeof(unsigned short)));
-      CK(cudaMemcpyAsync(ms.oc_tab, mi->oc_tables, mi->oc_table_count * sizeof(unsigned short),
+      CK(cudaMalloc(&ms.oc_tab, mi->oc->table_count * sizeof(unsigned short)));
+      CK(cudaMemcpyAsync(ms.oc_tab, mi->oc->tables, mi->oc->table_count * sizeof(unsigned short),
                          cudaMemcpyHostToDevice, st));
 #ifdef KPP_STRICT
       // strict build: the tail block of the LU factors is also written out, for the reference-order
       // backward substitution
-      ms.ws_bytes = (size_t)ms.blocks * mi->oc_tail * mi->oc_tail * sizeof(double);
+      ms.ws_bytes = (size_t)ms.blocks * mi->oc->tail * mi->oc->tail * sizeof(double);
       CK(cudaMalloc(&ms.ws, ms.ws_bytes));
 #endif
     } else {
@@ -199,9 +199,9 @@ int ensure_mech(DeviceState &d, int mech, const KppMechInfo *mi, int f32, cudaSt
   if (ms.coef_variant != f32) {
     double h[64];
     if (ms.onchip) {
-      if (mi->oc_nlit > 64) return fail(MISTRA_KPP_EINVAL, "coefficient table too large");
-      for (int i = 0; i < mi->oc_nlit; ++i) h[i] = literal_value(mi->oc_literals[i], f32);
-      CK(mi->oc_set_lit(h, st));
+      if (mi->oc->nlit > 64) return fail(MISTRA_KPP_EINVAL, "coefficient table too large");
+      for (int i = 0; i < mi->oc->nlit; ++i) h[i] = literal_value(mi->oc->literals[i], f32);
+      CK(mi->oc->set_lit(h, st));
     } else {
       if (mi->ncoef > 64) return fail(MISTRA_KPP_EINVAL, "coefficient table too large");
       for (int i = 0; i < mi->ncoef; ++i) h[i] = literal_value(mi->coef_literals[i], f32);
@@ -238,12 +238,14 @@ int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rcons
   if (slot == 1 && !ms.ws2 && ms.ws_bytes) CK(cudaMalloc(&ms.ws2, ms.ws_bytes));
   b.ws = slot ? ms.ws2 : ms.ws;
   b.oc_tab = ms.oc_tab;
+  b.oc_aux = nullptr;
+  b.oc_flags = 0;
   b.counter = d.counter + slot;
   CK(cudaStreamWaitEvent(st, d.ev_slot[slot], 0));
   CK(cudaMemsetAsync(b.counter, 0, sizeof(unsigned long long), st));
   if (ms.onchip) {
     int blocks = (int)(ncell < ms.blocks ? ncell : ms.blocks);
-    CK(mi->oc_launch(b, blocks, st));
+    CK(mi->oc->launch(b, blocks, st));
   } else {
     long long need_blocks = (ncell + KPP_BLOCK - 1) / KPP_BLOCK;
     int blocks = (int)(need_blocks < ms.blocks ? need_blocks : ms.blocks);

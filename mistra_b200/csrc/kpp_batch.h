@@ -24,10 +24,14 @@ struct KppBatch {
   double *ws;
   unsigned long long *counter;  // next unassigned cell, zeroed before launch
   const unsigned short *oc_tab; // on-chip kernels: instruction streams (device copy of the generated tables)
+  void *oc_aux;                 // on-chip kernels: spare pointer (diagnostics / experiments)
+  long long oc_flags;
   // decoded options (Rosenbrock_x, gas.f:950-1051)
   double t0, t1, rtol, atol, hmin, hmax, hstart, facmin, facmax, facrej, facsafe;
   int max_steps, autonomous;
 };
+
+struct KppOnchipInfo;   // csrc/kpp_onchip.h
 
 struct KppMechInfo {
   int nvar, nfix, nreact, lu_nonzero, nslot, ncoef;
@@ -35,16 +39,12 @@ struct KppMechInfo {
   const void *kernel;  // for occupancy queries
   cudaError_t (*launch)(const KppBatch &, int blocks, cudaStream_t);
   cudaError_t (*set_coef)(const double *host_coef, cudaStream_t);
-  // on-chip kernel (one thread block per cell, csrc/ros3_onchip.inc); oc_kernel == nullptr: not built
-  const void *oc_kernel;
-  cudaError_t (*oc_launch)(const KppBatch &, int blocks, cudaStream_t);
-  cudaError_t (*oc_set_lit)(const double *host_lit, cudaStream_t);
-  const unsigned short *oc_tables;   // host copy of the instruction streams
-  size_t oc_table_count;
-  const char *const *oc_literals;
-  int oc_nlit, oc_threads, oc_smem_bytes, oc_tail, oc_ctas_per_sm;
+  const KppOnchipInfo *oc;   // nullptr: this mechanism has no on-chip kernel
 };
 
+const KppOnchipInfo *kpp_onchip_info_g();
+const KppOnchipInfo *kpp_onchip_info_a();
+const KppOnchipInfo *kpp_onchip_info_t();
 const KppMechInfo *kpp_mech_info_g();
 const KppMechInfo *kpp_mech_info_a();
 const KppMechInfo *kpp_mech_info_t();

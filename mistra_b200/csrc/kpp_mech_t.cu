@@ -18,7 +18,7 @@ const KppMechInfo *kpp_mech_info_t()
   using namespace mech_t;
   static const KppMechInfo info = {NVAR, NFIX, NREACT, LU_NONZERO, NSLOT, NCOEF, coef_literals,
                                    (const void *)ros3_kernel_t, ros3_launch_t, set_coef,
-                                   nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, 0};
+                                   nullptr};
   return &info;
 }
 
