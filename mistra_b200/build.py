@@ -131,13 +131,15 @@ def build(verbose=False, strict=True, ptxas_v=False):
     return outs
 
 
-def build_variant(tag, extra_flags, units=("kpp_mech_a.cu",), verbose=False):
-    """Experiment build: libmistra_kpp_<tag>.so = the product objects with `units` recompiled
-    with extra nvcc flags (e.g. -DKPP_MIN_BLOCKS=3).  Select it at run time with
+def build_variant(tag, extra_flags, units=("kpp_mech_a.cu",), verbose=False, base="fast"):
+    """Experiment build: libmistra_kpp_<tag>.so = the product (base="fast") or strict (base="strict") objects
+    with `units` recompiled with extra nvcc flags (e.g. -DKPP_MIN_BLOCKS=3).  Select it at run time with
     MISTRA_KPP_LIB=libmistra_kpp_<tag>.so (mistra_b200/kpp.py)."""
+    bflags = ["-DKPP_STRICT", "-fmad=false"] if base == "strict" else []
     objs = []
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
-        jobs = [ex.submit(_compile, u % {"v": "fast"}, list(extra_flags) if u in units else [], tag if u in units else "fast", verbose)
+        jobs = [ex.submit(_compile, u % {"v": base}, bflags + (list(extra_flags) if u in units else []),
+                          tag if u in units else base, verbose)
                 for u in UNITS]
         objs = [j.result() for j in jobs]
     so = os.path.join(HERE, "libmistra_kpp_%s.so" % tag)
@@ -190,12 +192,15 @@ if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[1] == "--variant":
     # python -m mistra_b200.build --variant mb3 -DKPP_MIN_BLOCKS=3 [--units kpp_mech_a.cu,kpp_mech_g.cu]
     units = ("kpp_mech_a.cu",)
     flags = []
+    base = "fast"
     for a in sys.argv[3:]:
         if a.startswith("--units="):
             units = tuple(a.split("=", 1)[1].split(","))
+        elif a.startswith("--base="):
+            base = a.split("=", 1)[1]
         else:
             flags.append(a)
-    print(build_variant(sys.argv[2], flags, units, verbose=True))
+    print(build_variant(sys.argv[2], flags, units, verbose=True, base=base))
     sys.exit(0)
 
 if __name__ == "__main__":

@@ -18,6 +18,8 @@ namespace {
 std::mutex g_mu;
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+void *g_oc_aux = nullptr;      // development aid of the on-chip kernels (OC_DEBUG builds dump checkpoints here)
+long long g_oc_flags = 0;
 
 struct MechState {
   double *ws = nullptr;    // lane workspace of kernels on the caller's stream
@@ -238,8 +240,8 @@ int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rcons
   if (slot == 1 && !ms.ws2 && ms.ws_bytes) CK(cudaMalloc(&ms.ws2, ms.ws_bytes));
   b.ws = slot ? ms.ws2 : ms.ws;
   b.oc_tab = ms.oc_tab;
-  b.oc_aux = nullptr;
-  b.oc_flags = 0;
+  b.oc_aux = g_oc_aux;
+  b.oc_flags = g_oc_flags;
   b.counter = d.counter + slot;
   CK(cudaStreamWaitEvent(st, d.ev_slot[slot], 0));
   CK(cudaMemsetAsync(b.counter, 0, sizeof(unsigned long long), st));
@@ -483,6 +485,14 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
 }
 
 int64_t mistra_kpp_launch_count(void) { return g_launches.load(); }
+
+// Internal (not part of include/mistra_kpp.h): hands a device buffer and a flag word to the on-chip kernels;
+// only builds with -DOC_DEBUG / -DOC_PHASE_TIMERS look at them.
+extern "C" void mistra_kpp_oc_debug(void *dev_buffer, long long flags)
+{
+  g_oc_aux = dev_buffer;
+  g_oc_flags = flags;
+}
 
 int mistra_kpp_finalize(void)
 {

@@ -958,10 +958,11 @@ class Emitter:
         w("#define TL_MUL(x) ((x) * pv)")
         w("#define TL_SETDIAG(reg) reg = pv")
         w("#endif")
-        w("__device__ __forceinline__ void tail_lu(double (&a)[R][32], double *__restrict__ S, const unsigned w, const unsigned p)")
+        w("// (no __restrict__ on pointers into shared memory here: other threads write what this thread reads after a barrier)")
+        w("__device__ __forceinline__ void tail_lu(double (&a)[R][32], double *S, const unsigned w, const unsigned p)")
         w("{")
-        w("  double *__restrict__ lbuf = S + LBUF;")
-        w("  double *__restrict__ ubuf = S + UBUF + w * 64;")
+        w("  double *lbuf = S + LBUF;")
+        w("  double *ubuf = S + UBUF + w * 64;")
         w("  double l[R];")
         for kb in range(W):
             last = kb == W - 1
@@ -1043,7 +1044,7 @@ class Emitter:
         p, w = self.pf, self.w
         T, R, W, h = p.T, p.R, p.W, p.h
         w("// Forward substitution with the unit-lower tail block (ascending columns = KppSolve's order).")
-        w("__device__ __forceinline__ void tail_forward(const double (&a)[R][32], double *__restrict__ X, const double *__restrict__ XP,")
+        w("__device__ __forceinline__ void tail_forward(const double (&a)[R][32], double *X, const double *XP,")
         w("                                             const unsigned w, const unsigned p)")
         w("{")
         w("  double x[R];")
@@ -1069,7 +1070,7 @@ class Emitter:
         w("#ifndef KPP_STRICT")
         w("// Backward substitution with the upper tail block, column by column from the right; the diagonal")
         w("// registers hold reciprocal pivots.")
-        w("__device__ __forceinline__ void tail_backward(const double (&a)[R][32], double *__restrict__ X, const unsigned w, const unsigned p)")
+        w("__device__ __forceinline__ void tail_backward(const double (&a)[R][32], double *X, const unsigned w, const unsigned p)")
         w("{")
         w("  double x[R];")
         for wb in range(W - 1, -1, -1):
