@@ -173,6 +173,7 @@ int ensure_mech(DeviceState &d, int mech, const KppMechInfo *mi, int f32, cudaSt
       CK(cudaFuncSetAttribute(mi->oc->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mi->oc->smem_bytes));
       CK(cudaFuncSetAttribute(mi->oc->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mi->oc->kernel, mi->oc->threads, mi->oc->smem_bytes));
+      if (per_sm > 1) per_sm = 1;   // one persistent block per SM
     } else {
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mi->kernel, KPP_BLOCK, 0));
     }
@@ -189,7 +190,7 @@ int ensure_mech(DeviceState &d, int mech, const KppMechInfo *mi, int f32, cudaSt
 #ifdef KPP_STRICT
       // strict build: the tail block of the LU factors is also written out, for the reference-order
       // backward substitution
-      ms.ws_bytes = (size_t)ms.blocks * mi->oc->tail * mi->oc->tail * sizeof(double);
+      ms.ws_bytes = (size_t)ms.blocks * mi->oc->slots * mi->oc->tail * mi->oc->tail * sizeof(double);
       CK(cudaMalloc(&ms.ws, ms.ws_bytes));
 #endif
     } else {
@@ -246,7 +247,8 @@ int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rcons
   CK(cudaStreamWaitEvent(st, d.ev_slot[slot], 0));
   CK(cudaMemsetAsync(b.counter, 0, sizeof(unsigned long long), st));
   if (ms.onchip) {
-    int blocks = (int)(ncell < ms.blocks ? ncell : ms.blocks);
+    const long long need = (ncell + mi->oc->slots - 1) / mi->oc->slots;
+    int blocks = (int)(need < ms.blocks ? need : ms.blocks);
     CK(mi->oc->launch(b, blocks, st));
   } else {
     long long need_blocks = (ncell + KPP_BLOCK - 1) / KPP_BLOCK;
@@ -431,7 +433,7 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
   // Host buffers may be pageable (Fortran arrays) or pinned; cudaMemcpyAsync handles
   // both, only pinned ones actually overlap.
   if ((rc = ensure_mech(*d, mech, mi, o ? (o->f32_literals ? 1 : 0) : 1, st))) return rc;
-  const int64_t resident = (int64_t)d->mech[mech].blocks * (d->mech[mech].onchip ? 8 : KPP_BLOCK);
+  const int64_t resident = (int64_t)d->mech[mech].blocks * (d->mech[mech].onchip ? mi->oc->slots : KPP_BLOCK);
   int64_t nchunk = ncell / (2 * resident);
   if (nchunk < 1) nchunk = 1;
   if (nchunk > 16) nchunk = 16;

@@ -2,7 +2,7 @@
 #pragma once
 #include "kpp_batch.h"
 
-// on-chip kernel of a mechanism (one thread block per cell, csrc/ros3_onchip.inc, csrc/kpp_onchip_<x>.cu)
+// on-chip kernel of a mechanism (one persistent block per SM with `slots` cells in flight)
 struct KppOnchipInfo {
   const void *kernel;
   cudaError_t (*launch)(const KppBatch &, int blocks, cudaStream_t);
@@ -10,6 +10,6 @@ struct KppOnchipInfo {
   const unsigned short *tables;   // host copy of the instruction streams
   size_t table_count;
   const char *const *literals;
-  int nlit, threads, smem_bytes, tail, ctas_per_sm;
+  int nlit, threads, smem_bytes, tail, slots;
 };
 

@@ -9,7 +9,8 @@ Design: a cell's whole integrator state stays on the SM for the
   tail-column part of the head rows) is sparse and irregular; it lives in shared
   memory as a compact list ``G`` (head diagonals first, then the reference's CSR order
   without the tail block) and is processed by small table-driven interpreters whose
-  instruction streams come from global memory through a per-warp TMA ring;
+  instruction streams come from global memory through the block's TMA pipeline (one copy serves all cell
+  slots of the block);
 * the *tail* (the trailing T x T block, 83-95 % dense after fill-in) lives in
   REGISTERS: lane p of warp w holds rows ``h+p+32q`` (q < R) and columns
   ``h+32w .. h+32w+31`` as ``a[q][s]``; its elimination, the head->tail updates and
@@ -47,7 +48,7 @@ import numpy as np
 
 from . import mech as mechmod
 
-CHUNK = 16         # 16-bit stream words per thread and ring stage (32 bytes)
+CHUNK = 16         # 16-bit stream words per thread and pipeline stage (32 bytes)
 FUN_GS, JAC_GS = 8, 4
 F_BEGIN, F_STORE, F_SCALE = 1, 2, 4
 F_WSYNC, F_CSYNC, F_PARTIAL = 1, 2, 4
@@ -158,9 +159,9 @@ class Plan:
         self.nex = max(0, need_jac, need_fun, need_lu, need_xp)
         o += self.nex
         o += o & 1
-        self.O_RING = o; o += self.W * 2 * CHUNK * 32 * 2 // 8     # per warp: 2 stages x CHUNK words x 32 lanes
-        self.O_MISC = o; o += 12 + 3 * self.W                       # integrator state, reduction scratch, mbarriers
-        self.smem_doubles = o
+        self.O_MISC = o; o += 12 + self.W                           # integrator state, reduction scratch, RCONST mbarrier
+        o += o & 1
+        self.smem_doubles = o                                       # one cell slot; the block adds the stream pipeline
         assert o < 8192
         assert m.nreact + 2 <= self.NG, "RCONST staging for the Jacobian does not fit in G"
 
@@ -185,36 +186,23 @@ class Plan:
         """Values of the constant operands that follow V in shared memory."""
         return np.concatenate([np.asarray(fix, dtype=np.float64), self.lit_values(f32), [1.0]])
 
-    def _pack16(self, per_thread, per_warp_len=False):
-        """per_thread[t] = list of 16-bit words.  Returns (flat uint16 array, nchunk[w]): every warp's
-        stream is padded to a multiple of CHUNK words per thread (all warps to the same length unless
-        per_warp_len) and stored as [w][chunk][half][lane][8] (a stage of 1 KiB is contiguous; a thread's
-        two 16-byte items sit at [half][lane]: conflict-free 128-bit shared loads)."""
-        Lw = []
-        for w in range(self.W):
-            L = max(len(per_thread[32 * w + p]) for p in range(32))
-            Lw.append(max(CHUNK, (L + CHUNK - 1) // CHUNK * CHUNK))
-        if not per_warp_len:
-            Lw = [max(Lw)] * self.W
-        parts = []
-        for w in range(self.W):
-            a = np.zeros((32, Lw[w]), dtype=np.uint16)
-            for p in range(32):
-                ws = per_thread[32 * w + p]
-                a[p, :len(ws)] = ws
-            a = a.reshape(32, Lw[w] // CHUNK, 2, 8).transpose(1, 2, 0, 3)
-            parts.append(np.ascontiguousarray(a).reshape(-1))
-        return np.concatenate(parts), [L // CHUNK for L in Lw]
+    def _pack16(self, per_thread):
+        """per_thread[t] = list of 16-bit words.  Returns (flat uint16 array, nchunk): every thread's stream is
+        padded to the same multiple of CHUNK words and stored as [chunk][w][half][lane][8]: a chunk (W KiB) is
+        what one stage of the block's stream pipeline holds; warp w reads its 1 KiB piece, a thread's two
+        16-byte items sit at [half][lane] (conflict-free 128-bit shared loads)."""
+        L = max(len(x) for x in per_thread)
+        L = max(CHUNK, (L + CHUNK - 1) // CHUNK * CHUNK)
+        a = np.zeros((self.NT, L), dtype=np.uint16)
+        for t in range(self.NT):
+            ws = per_thread[t]
+            a[t, :len(ws)] = ws
+        a = a.reshape(self.W, 32, L // CHUNK, 2, 8).transpose(2, 0, 3, 1, 4)
+        return np.ascontiguousarray(a).reshape(-1), L // CHUNK
 
     def unpack16(self, flat, nchunk):
-        out = []
-        o = 0
-        for w in range(self.W):
-            cnt = nchunk[w] * CHUNK * 32
-            a = flat[o:o + cnt].reshape(nchunk[w], 2, 32, 8).transpose(2, 0, 1, 3).reshape(32, -1)
-            out += [a[p] for p in range(32)]
-            o += cnt
-        return out
+        a = flat.reshape(nchunk, self.W, 2, 32, 8).transpose(1, 3, 0, 2, 4).reshape(self.NT, -1)
+        return [a[t] for t in range(self.NT)]
 
     # ---- rate products -----------------------------------------------------------------
     def _prod_words(self, r, refs, dst):
@@ -454,42 +442,27 @@ class Plan:
 
     def _schedule(self, levels, warp0_only):
         """levels = list of lists of pieces (piece = list of frames).  Returns per-thread word lists.
-        Levels listed in warp0_only are run by warp 0 alone, separated by warp barriers; the others
-        are spread over all threads and separated by block barriers."""
+        Levels listed in warp0_only are run by warp 0 alone (the other warps idle through empty frames) and
+        are closed by a warp barrier when the next level is warp 0's too; all other levels are spread over
+        all threads and closed by a barrier of the cell's threads.  Every thread's stream has the same
+        length at every barrier, so the warps of a cell stay within one chunk of each other."""
         per = [[] for _ in range(self.NT)]
         nul = [0, self.ZERO << 3] + [0] * NENT
-
-        def close(ts, flag):
-            """pad every warp touched by ts to its own longest lane; flag the last frame"""
-            for w in sorted(set(t >> 5 for t in ts)):
-                lanes = [t for t in ts if (t >> 5) == w]
-                L = max(len(per[t]) for t in lanes)
-                for t in lanes:
-                    while len(per[t]) < L:
-                        per[t] += nul
-                    per[t][len(per[t]) - 8 + 1] |= flag
+        allt = list(range(self.NT))
         for li, pieces in enumerate(levels):
             w0 = li in warp0_only
-            ts = list(range(32)) if w0 else list(range(self.NT))
-            base = {t: len(per[t]) for t in ts}
+            ts = list(range(32)) if w0 else allt
             who, _ = _lpt([len(p) for p in pieces], len(ts))
             for k in sorted(range(len(pieces)), key=lambda k: -len(pieces[k])):
                 for fr in pieces[k]:
                     per[ts[who[k]]] += fr
-            for t in ts:                              # at least one frame carries the barrier flag
-                if len(per[t]) == base[t]:
+            L = max(len(per[t]) for t in allt)
+            for t in allt:
+                while len(per[t]) < L:
                     per[t] += nul
-            nxt_w0 = (li + 1) in warp0_only
-            if w0 and nxt_w0:
-                close(ts, F_WSYNC)
-            else:
-                if w0:                                 # the other warps join at the block barrier
-                    for t in range(32, self.NT):
-                        per[t] += nul
-                close(list(range(self.NT)) if not w0 else ts, F_CSYNC)
-                if w0:
-                    for t in range(32, self.NT):
-                        per[t][len(per[t]) - 8 + 1] |= F_CSYNC
+            flag = F_WSYNC if (w0 and (li + 1) in warp0_only) else F_CSYNC
+            for t in allt:
+                per[t][len(per[t]) - 8 + 1] |= flag
         return per
 
     def _build_solve(self):
@@ -525,7 +498,7 @@ class Plan:
         small = set(i for i, p in enumerate(head_levels) if len(p) <= 40) if self.W > 1 else set()
         per = self._schedule(lv, small)
         self.fwd_levels = lv
-        self.fwd_stream, self.fwd_nchunk = self._pack16(per, per_warp_len=True)
+        self.fwd_stream, self.fwd_nchunk = self._pack16(per)
         # ---- backward: head rows (the tail block is solved first)
         #   strict: reference order (ascending columns, then the division)
         #   fast:   tail columns first (known once the tail is solved), then head columns by level
@@ -551,7 +524,7 @@ class Plan:
         small = set(i for i, p in enumerate(lv) if i > 0 and len(p) <= 40) if self.W > 1 else set()
         per = self._schedule(lv, small)
         self.bwd_levels = lv
-        self.bwd_stream, self.bwd_nchunk = self._pack16(per, per_warp_len=True)
+        self.bwd_stream, self.bwd_nchunk = self._pack16(per)
 
     # =============================================================================================
     # CPU emulation (numpy, IEEE double, no fused multiply-add): same order as the kernel
@@ -822,23 +795,18 @@ STREAMS = ("funs", "funp", "fun", "jacp", "jt", "jfill", "jh", "jlate", "hop", "
 
 
 def table_blob(p):
-    """All streams of a plan in one uint16 array; returns (blob, desc) with desc[name] = (off[w], nchunk[w]);
-    offsets in uint16 units, every warp stream 1 KiB aligned."""
+    """All streams of a plan in one uint16 array; returns (blob, desc) with desc[name] = (first chunk, number of
+    chunks); a chunk = W KiB = CHUNK words for each of the cell's threads."""
     parts = []
     desc = {}
     o = 0
     for name in STREAMS:
         flat = getattr(p, name + "_stream")
         nch = getattr(p, name + "_nchunk")
-        offs = []
-        oo = o
-        for w in range(p.W):
-            offs.append(oo)
-            oo += nch[w] * CHUNK * 32
-        desc[name] = (offs, list(nch))
+        assert len(flat) == nch * CHUNK * p.NT
+        desc[name] = (o, nch)
         parts.append(flat)
-        o += len(flat)
-        assert oo == o
+        o += nch
     return np.concatenate(parts), desc
 
 
@@ -876,7 +844,7 @@ class Emitter:
         w("constexpr int NVAR = %d, NFIX = %d, NREACT = %d, LU_NONZERO = %d, BDIM = %d;" % (m.nvar, m.nfix, m.nreact, m.lu_nonzero, m.bdim))
         w("constexpr int T = %d, R = %d, W = %d, NT = %d, HEAD = %d, NG = %d, ZERO = %d, NGP = %d;" % (p.T, p.R, p.W, p.NT, p.h, p.NG, p.ZERO, p.NGP))
         w("constexpr int NC = %d, NLIT = %d;" % (p.nc, p.nlit))
-        for k in ("O_G", "O_Y", "O_CY", "O_T1", "O_CT", "O_K1", "O_K2", "O_K3", "O_EX", "O_RING", "O_MISC"):
+        for k in ("O_G", "O_Y", "O_CY", "O_T1", "O_CT", "O_K1", "O_K2", "O_K3", "O_EX", "O_MISC"):
             w("constexpr int %s = %d;" % (k, getattr(p, k)))
             assert getattr(self.ps, k) == getattr(p, k)
         assert self.ps.smem_doubles == p.smem_doubles
@@ -889,10 +857,9 @@ class Emitter:
             w(tag)
             blob, desc = table_blob(pl)
             w("constexpr unsigned TABLE_COUNT = %d;" % len(blob))
-            w("__constant__ unsigned c_st_off[ST_COUNT][W] = {%s};" % ", ".join(
-                "{" + ",".join(str(o) for o in desc[n][0]) + "}" for n in STREAMS))
-            w("__constant__ unsigned c_st_nchunk[ST_COUNT][W] = {%s};" % ", ".join(
-                "{" + ",".join(str(o) for o in desc[n][1]) + "}" for n in STREAMS))
+            w("// first chunk / number of chunks of every stream (a chunk = W KiB)")
+            w("__constant__ unsigned c_st_off[ST_COUNT] = {%s};" % ", ".join(str(desc[n][0]) for n in STREAMS))
+            w("__constant__ unsigned c_st_nchunk[ST_COUNT] = {%s};" % ", ".join(str(desc[n][1]) for n in STREAMS))
             for q in range(pl.R):
                 w("#define FWD_PARTIAL_%d 0x%xu" % (q, sum((1 << pp) for pp in range(32) if pl.fwd_partial[pp + 32 * q])))
         w("#endif")
@@ -903,6 +870,9 @@ class Emitter:
         w("__device__ const unsigned short d_rowbase[T] = {%s};" % ",".join(str(int(v)) for v in p.rowbase))
         w("// keeps the compiler from hoisting a whole pivot row into registers (the tail already fills them)")
         w("#define OC_SCHED_FENCE() __syncwarp()")
+        w("// barrier of one cell slot of the block (named barrier 1 + slot, the NT threads that own the cell)")
+        w("__device__ __forceinline__ void oc_slot_sync(unsigned id) { asm volatile(\"bar.sync %0, %1;\" ::\"r\"(id), \"n\"(NT) : \"memory\"); }")
+        w("#define OC_SLOT_SYNC() oc_slot_sync(slot_bar)")
         w("")
         self.emit_ht()
         self.emit_tail_lu()
@@ -959,7 +929,7 @@ class Emitter:
         w("#define TL_SETDIAG(reg) reg = pv")
         w("#endif")
         w("// (no __restrict__ on pointers into shared memory here: other threads write what this thread reads after a barrier)")
-        w("__device__ __forceinline__ void tail_lu(double (&a)[R][32], double *S, const unsigned w, const unsigned p)")
+        w("__device__ __forceinline__ void tail_lu(double (&a)[R][32], double *S, const unsigned w, const unsigned p, const unsigned slot_bar)")
         w("{")
         w("  double *lbuf = S + LBUF;")
         w("  double *ubuf = S + UBUF + w * 64;")
@@ -981,7 +951,7 @@ class Emitter:
                 if not last:
                     for q in range(kb, R):
                         w("      lbuf[%d + p] = l[%d];" % (par * T + 32 * q, q))
-                    w("      __syncthreads();")
+                    w("      OC_SLOT_SYNC();")
                 if ks < 31:
                     s0 = ks + 1
                     w("      if (p == %du) {" % ks)
@@ -1015,7 +985,7 @@ class Emitter:
                 w("  else if (w > %d) {" % kb)
                 w("    for (unsigned ks = 0; ks < 32u; ++ks) {")
                 w("      const unsigned par = ks & 1u;")
-                w("      __syncthreads();")
+                w("      OC_SLOT_SYNC();")
                 for q in range(kb, R):
                     w("      l[%d] = lbuf[par * %d + %d + p];" % (q, T, 32 * q))
                 w("      if (p == ks) {")
@@ -1034,7 +1004,7 @@ class Emitter:
                 w("  }")
                 if kb > 0:
                     w("  else {")
-                    w("    for (unsigned ks = 0; ks < 32u; ++ks) __syncthreads();")
+                    w("    for (unsigned ks = 0; ks < 32u; ++ks) OC_SLOT_SYNC();")
                     w("  }")
         w("}")
         w("")
@@ -1045,7 +1015,7 @@ class Emitter:
         T, R, W, h = p.T, p.R, p.W, p.h
         w("// Forward substitution with the unit-lower tail block (ascending columns = KppSolve's order).")
         w("__device__ __forceinline__ void tail_forward(const double (&a)[R][32], double *X, const double *XP,")
-        w("                                             const unsigned w, const unsigned p)")
+        w("                                             const unsigned w, const unsigned p, const unsigned slot_bar)")
         w("{")
         w("  double x[R];")
         for wb in range(W):
@@ -1064,13 +1034,13 @@ class Emitter:
             for q in range(wb, R):
                 w("    X[%d + p] = x[%d];" % (h + 32 * q, q))
             w("  }")
-            w("  __syncthreads();")
+            w("  OC_SLOT_SYNC();")
         w("}")
         w("")
         w("#ifndef KPP_STRICT")
         w("// Backward substitution with the upper tail block, column by column from the right; the diagonal")
         w("// registers hold reciprocal pivots.")
-        w("__device__ __forceinline__ void tail_backward(const double (&a)[R][32], double *X, const unsigned w, const unsigned p)")
+        w("__device__ __forceinline__ void tail_backward(const double (&a)[R][32], double *X, const unsigned w, const unsigned p, const unsigned slot_bar)")
         w("{")
         w("  double x[R];")
         for wb in range(W - 1, -1, -1):
@@ -1088,7 +1058,7 @@ class Emitter:
             for q in range(0, wb + 1):
                 w("    X[%d + p] = x[%d];" % (h + 32 * q, q))
             w("  }")
-            w("  __syncthreads();")
+            w("  OC_SLOT_SYNC();")
         w("}")
         w("#endif")
         w("")

@@ -10,7 +10,7 @@ multiply-add), against the CPU oracle's building blocks:
 
 Also checks the structural invariants the kernel relies on: block barriers at the same position in
 every warp's stream, no two operations of an elimination wave touching the same slot, the shared
-memory budget of five (aer) / sixteen (gas) resident blocks per SM."""
+memory budget of five (aer) / fifteen (gas) cell slots per block."""
 import numpy as np
 import pytest
 
@@ -120,9 +120,9 @@ def test_block_barriers_line_up(plans):
 
 
 def test_shared_memory_budget(plans):
+    """One persistent block per SM: the cell slots + the 8-stage stream pipeline + barriers fit in 227 KiB."""
     mi, name, m, ps, pf = plans
-    per_sm = 233472
-    ctas = {"gas": 16, "aer": 5}[name]
+    slots = {"gas": 15, "aer": 5}[name]
     for p in (ps, pf):
-        assert ctas * (p.smem_doubles * 8 + 1024) <= per_sm
-        assert p.smem_doubles == ps.smem_doubles
+        assert slots * p.smem_doubles * 8 + 8 * 1024 * p.W + 2 * 8 * 8 + 2 * slots * 4 + 16 <= 232448
+        assert p.smem_doubles == ps.smem_doubles and p.smem_doubles % 2 == 0

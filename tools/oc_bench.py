@@ -41,6 +41,14 @@ def main():
     d_ierr = torch.zeros(ens.ncell, dtype=torch.int32, device="cuda")
     d_stats = torch.zeros((ens.ncell, 8), dtype=torch.int32, device="cuda")
     times = []
+    ph = None
+    if os.environ.get("OC_PHASES"):
+        import ctypes as C
+        ph = torch.zeros(16, dtype=torch.int64, device="cuda")
+        L = kpp.library()
+        L.mistra_kpp_oc_debug.argtypes = [C.c_void_p, C.c_longlong]
+        L.mistra_kpp_oc_debug.restype = None
+        L.mistra_kpp_oc_debug(C.c_void_p(ph.data_ptr()), 0)
     for it in range(4):
         d_var.copy_(d_var0)
         torch.cuda.synchronize()
@@ -59,6 +67,14 @@ def main():
     print("%s onchip=%s: %.3f ms (%s), %.3f M cells/s, %.2f M steps/s, nstp/cell %.2f, nrej %d, %.2f TFLOP/s = %.3f of FP64 peak %.1f"
           % (name, os.environ.get("MISTRA_KPP_ONCHIP", "1"), ms, ",".join("%.1f" % t for t in times), ens.ncell / ms / 1e3,
              nstp / ms / 1e3, nstp / ens.ncell, nrej, flop / ms / 1e9, flop / ms / 1e9 / peak, peak), flush=True)
+    if ph is not None:
+        v = ph.cpu().numpy().astype(np.float64) / 4.0 / max(1, nstp)       # 4 timed launches
+        names = ["jacprep", "fun K1", "hops", "ht", "tail_lu", "fwd frames", "tail fwd", "tail bwd", "bwd frames", "fun stage2 + rhs",
+                 "combos/errnorm/ctl", "cell load/store"]
+        tot = v[:12].sum()
+        print("cycles per Ros3 step and cell (thread 0 of each block): total %.0f" % tot)
+        for n_, x in zip(names, v):
+            print("  %-20s %9.0f  %5.1f %%" % (n_, x, 100 * x / tot))
     if check:
         from oracle import kpp_oracle as ko
         idx = np.linspace(0, ens.ncell - 1, min(check, ens.ncell)).astype(np.int64)
