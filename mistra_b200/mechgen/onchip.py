@@ -140,10 +140,12 @@ class Plan:
         o += o & 1
         self.O_T1 = o; o += n
         self.O_CT = o; o += self.nc
-        self.O_K1 = o; o += n
+        # every K vector is followed by a slot that holds 0.0 while the vector is being solved for: padded
+        # entries of the substitution frames point there (x = 0), so the frames run without branches
+        self.O_K1 = o; o += n + 1
         o += o & 1
-        self.O_K2 = o; o += n          # 16-byte aligned: RCONST is staged here by a bulk copy
-        self.O_K3 = o; o += n
+        self.O_K2 = o; o += n + 1      # 16-byte aligned: RCONST is staged here by a bulk copy
+        self.O_K3 = o; o += n + 1
         self.O_EX = o
         # Fun: [K2..EX) holds RCT/A (in place, shifted by <= 1), the scaled copies, a zero and a dump slot
         self.fun_nscr = m.nreact + 1 + len(self.fun_scaled) + 2
@@ -437,7 +439,7 @@ class Plan:
                 if scale:
                     h0 |= F_SCALE
             h1 = ((gp + f * NENT) << 3) | (F_PARTIAL if partial else 0)
-            out.append([h0, h1] + [(c << 3) | 1 for c in part] + [0] * (NENT - len(part)))
+            out.append([h0, h1] + [(c << 3) | 1 for c in part] + [self.n << 3] * (NENT - len(part)))
         return out
 
     def _schedule(self, levels, warp0_only):
@@ -447,7 +449,7 @@ class Plan:
         all threads and closed by a barrier of the cell's threads.  Every thread's stream has the same
         length at every barrier, so the warps of a cell stay within one chunk of each other."""
         per = [[] for _ in range(self.NT)]
-        nul = [0, self.ZERO << 3] + [0] * NENT
+        nul = [0, self.ZERO << 3] + [self.n << 3] * NENT
         allt = list(range(self.NT))
         for li, pieces in enumerate(levels):
             w0 = li in warp0_only
