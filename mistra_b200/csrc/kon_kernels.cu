@@ -533,7 +533,8 @@ kon_subkon_kernel(KonGridDev g, long long ncell, double dt, KonArgs A, int rch)
 }
 
 // ---- host side ---------------------------------------------------------------------------
-std::mutex g_mu;
+// recursive: the host-buffer wrappers hold it across their scratch handling and the launch (launch() takes it too)
+std::recursive_mutex g_mu;
 std::atomic<long long> g_launches{0};
 
 struct GridCache {
@@ -671,7 +672,7 @@ int launch(const mistra_kon_grid *g, int64_t ncell, double dt, const KonArgs &A,
   const int rch = rows_per_chunk(g);
   if (rch < 1) return mistra_internal_fail(MISTRA_KPP_EINVAL, "grid too large for shared memory");
   const size_t smem = smem_bytes(g) + (((size_t)rch * ((size_t)g->nkt * 10 + 8) + 31) & ~(size_t)15);
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   cudaStream_t st = (cudaStream_t)stream;
   KonGridDev gd;
   GridCache *gc;
@@ -728,6 +729,9 @@ int mistra_kon_subkon(const mistra_kon_grid *g, int64_t ncell, double dt, double
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)ncell, b_ff = n * g->nka * g->nkt * 8, b_tr = n * MB * 8, b_s = n * 8, b_i = n * 4;
   const size_t total = b_ff + b_tr + 7 * b_s + 2 * b_i + 64;
+  // the per-device scratch buffer is grown, filled and read back under the lock: two host threads on the same
+  // device must not free it under each other's copies
+  std::lock_guard<std::recursive_mutex> lk_scratch(g_mu);
   Scratch &sc = g_scratch[dev];
   if (sc.bytes < total) {
     if (sc.p) { CKK(cudaDeviceSynchronize()); cudaFree(sc.p); sc.p = nullptr; sc.bytes = 0; }
@@ -818,6 +822,9 @@ int mistra_kon_layers(const mistra_kon_grid *g, int64_t ncell, double dt, int ch
   size_t total = 0;
   for (auto &it : items)
     if (it.h) total += (it.bytes + 255) & ~(size_t)255;
+  // the per-device scratch buffer is grown, filled and read back under the lock: two host threads on the same
+  // device must not free it under each other's copies
+  std::lock_guard<std::recursive_mutex> lk_scratch(g_mu);
   Scratch &sc = g_scratch[dev];
   if (sc.bytes < total) {
     if (sc.p) { CKK(cudaDeviceSynchronize()); cudaFree(sc.p); sc.p = nullptr; sc.bytes = 0; }
