@@ -110,6 +110,15 @@ double mistra_kpp_fp64_peak_tflops(void);
 /* Kernels launched by this library since load (the bench's gpu_launches claim). */
 int64_t mistra_kpp_launch_count(void);
 
+/* Kernel variant of a mechanism (a tuning knob, results agree within the parity contract):
+ *   0  one cell per thread, per-lane workspace in HBM (csrc/ros3_kernel.inc) - the default, fastest on B200 today;
+ *   1  on-chip kernel (csrc/ros3_onchip.inc): one persistent block per SM, cell slots in lockstep, the sparse head of
+ *      the LU factors in shared memory, the dense tail in registers, DRAM traffic = compulsory I/O.  gas and aer only.
+ * Takes effect at the next integrate call (workspaces are re-allocated).  MISTRA_KPP_ONCHIP=1 in the environment
+ * makes 1 the default where it exists.  Returns 0 or a negative MISTRA_KPP_E* code. */
+int mistra_kpp_set_kernel(int mech, int variant);
+int mistra_kpp_get_kernel(int mech);
+
 /* Release device workspaces, pinned staging buffers and the library stream. */
 int mistra_kpp_finalize(void);
 

@@ -154,20 +154,32 @@ double literal_value(const char *lit, int f32)
   return f32 ? (double)strtof(lit, nullptr) : strtod(lit, nullptr);
 }
 
-// MISTRA_KPP_ONCHIP=0 selects the round-1 mapping (one cell per thread, workspace in HBM) where an
-// on-chip kernel exists - for A/B measurements only; both are CUDA paths, there is no CPU path.
-bool want_onchip(const KppMechInfo *mi)
+// Kernel variant of a mechanism: 0 = one cell per thread with the lane workspace in HBM (ros3_kernel.inc, the
+// faster one on B200 today and the default), 1 = the on-chip kernel (ros3_onchip.inc: one persistent block per
+// SM, LU in shared memory / registers, DRAM traffic = the compulsory I/O).  Chosen per mechanism with
+// mistra_kpp_set_kernel(); MISTRA_KPP_ONCHIP=1 in the environment makes 1 the default where it exists.
+// Both are CUDA paths, there is no CPU path.
+int g_variant[3] = {-1, -1, -1};
+bool want_onchip(const KppMechInfo *mi, int mech)
 {
   if (!mi->oc) return false;
+  if (g_variant[mech] >= 0) return g_variant[mech] == 1;
   const char *e = getenv("MISTRA_KPP_ONCHIP");
-  return !(e && atoi(e) == 0);
+  return e && atoi(e) == 1;
 }
 
 int ensure_mech(DeviceState &d, int mech, const KppMechInfo *mi, int f32, cudaStream_t st)
 {
   MechState &ms = d.mech[mech];
+  if ((ms.ws || ms.oc_tab) && ms.onchip != want_onchip(mi, mech)) {   // the variant was switched: start over
+    CK(cudaDeviceSynchronize());
+    if (ms.ws) cudaFree(ms.ws);
+    if (ms.ws2) cudaFree(ms.ws2);
+    if (ms.oc_tab) cudaFree(ms.oc_tab);
+    ms = MechState();
+  }
   if (!ms.ws && !ms.oc_tab) {
-    ms.onchip = want_onchip(mi);
+    ms.onchip = want_onchip(mi, mech);
     int per_sm = 0;
     if (ms.onchip) {
       CK(cudaFuncSetAttribute(mi->oc->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mi->oc->smem_bytes));
@@ -362,7 +374,7 @@ int mistra_kpp_integrate_device(int mech, int64_t ncell, const double *d_rconst,
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream, as in the CUDA runtime
   // Experiment (MISTRA_KPP_SPLIT=1): the two halves of a long batch as two co-resident kernels.
   static const bool split = getenv("MISTRA_KPP_SPLIT") && atoi(getenv("MISTRA_KPP_SPLIT")) > 0;
-  if (split && !want_onchip(mech_info(mech)) && ncell >= 8LL * d->num_sm * 2 * KPP_BLOCK) {
+  if (split && !want_onchip(mech_info(mech), mech) && ncell >= 8LL * d->num_sm * 2 * KPP_BLOCK) {
     const KppMechInfo *mi = mech_info(mech);
     if ((rc = ensure_streams(d))) return rc;
     const int64_t h = ncell / 2;
@@ -487,6 +499,22 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
 }
 
 int64_t mistra_kpp_launch_count(void) { return g_launches.load(); }
+
+int mistra_kpp_set_kernel(int mech, int variant)
+{
+  if (mech < 0 || mech > 2) return fail(MISTRA_KPP_EINVAL, "mech must be 0, 1 or 2");
+  if (variant < 0 || variant > 1) return fail(MISTRA_KPP_EINVAL, "variant must be 0 (cell per thread) or 1 (on-chip)");
+  if (variant == 1 && !mech_info(mech)->oc) return fail(MISTRA_KPP_EINVAL, "this mechanism has no on-chip kernel");
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_variant[mech] = variant;
+  return 0;
+}
+
+int mistra_kpp_get_kernel(int mech)
+{
+  if (mech < 0 || mech > 2) return fail(MISTRA_KPP_EINVAL, "mech must be 0, 1 or 2");
+  return want_onchip(mech_info(mech), mech) ? 1 : 0;
+}
 
 // Internal (not part of include/mistra_kpp.h): hands a device buffer and a flag word to the on-chip kernels;
 // only builds with -DOC_DEBUG / -DOC_PHASE_TIMERS look at them.

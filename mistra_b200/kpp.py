@@ -156,6 +156,16 @@ def integrate_device(mech, rconst, fix, var, t0=0.0, t1=10.0, opts=None, ierr=No
     _check(L, rc)
 
 
+def set_kernel(mech, variant, strict=False):
+    """Kernel variant of a mechanism: 0 = one cell per thread (default), 1 = on-chip (gas, aer)."""
+    L = library(strict)
+    _check(L, L.mistra_kpp_set_kernel(mech, variant))
+
+
+def get_kernel(mech, strict=False):
+    return int(library(strict).mistra_kpp_get_kernel(mech))
+
+
 def launch_count(strict=False):
     return int(library(strict).mistra_kpp_launch_count())
 

@@ -21,7 +21,9 @@ MECHS = list(enumerate(mechmod.MECH_NAMES))
 
 
 def compare(out, ref, stats, stats_o, ierr, ierr_o, hexit, hexit_o, locked_tol=1e-9, hexit_rtol=1e-7):
-    assert np.array_equal(ierr, ierr_o)
+    bad = np.nonzero(ierr != ierr_o)[0]
+    assert bad.size == 0, "ierr differs in %d cells, first %s: %s vs oracle %s, stats %s vs %s" % (
+        bad.size, bad[:6], ierr[bad[:6]], ierr_o[bad[:6]], stats[bad[:1]], stats_o[bad[:1]])
     # failed cells (ierr < 0) return a partially advanced VAR (gas.f:764-770); they are
     # counted, not compared (SURVEY 8a trap 9: their path runs through non-finite norms)
     ok = ierr == 1

@@ -2,7 +2,7 @@
 
   python tools/oc_bench.py [gas|aer|tot] [ncol] [spinup] [check]
 
-MISTRA_KPP_ONCHIP=0 selects the round-1 cell-per-thread mapping.  Prints cells/s, Ros3 steps/s,
+MISTRA_KPP_ONCHIP=0 selects the default cell-per-thread kernel, 1 (default of this tool) the on-chip variant.  Prints cells/s, Ros3 steps/s,
 the FP64 roofline fraction (SURVEY 8d flop table) and, with check > 0, the parity of `check`
 cells of the timed output against the CPU oracle.
 """
@@ -27,6 +27,8 @@ def main():
     cls = {"gas": synthetic.GasEnsemble, "aer": synthetic.AerEnsemble, "tot": synthetic.TotEnsemble}[name]
     ens = cls(ncol)
     mech = {"gas": 0, "aer": 1, "tot": 2}[name]
+    variant = int(os.environ.get("MISTRA_KPP_ONCHIP", "1")) if mech < 2 else 0
+    kpp.set_kernel(mech, variant)
     var = ens.var.copy()
     t0 = time.time()
     for _ in range(spin):

@@ -41,6 +41,7 @@ def main():
         return emulate(p, D, var, fix, rc, cell)
     buf = torch.full((NCHK, per), float("nan"), dtype=torch.float64, device="cuda")
     L = kpp.library()
+    kpp.set_kernel(mech, 1)
     L.mistra_kpp_oc_debug.argtypes = [C.c_void_p, C.c_longlong]
     L.mistra_kpp_oc_debug.restype = None
     L.mistra_kpp_oc_debug(C.c_void_p(buf.data_ptr()), cell)
