@@ -27,6 +27,7 @@
 #ifndef MISTRA_KPP_H
 #define MISTRA_KPP_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -108,6 +109,25 @@ int mistra_kpp_integrate_device(int mech, int64_t ncell, const double *d_rconst,
 double mistra_kpp_fp64_peak_tflops(void);
 
 /* Kernels launched by this library since load (the bench's gpu_launches claim). */
+/* The same call over several GPUs of the box from ONE process (what a Fortran kpp_driver needs to reach all 8 GPUs,
+ * kpp.f90:4294-4310): the cells are cut into `ndev` contiguous slices, slice i runs on CUDA device devices[i]
+ * (devices == NULL: 0..ndev-1; ndev <= 0: every visible device) through mistra_kpp_integrate on its own host
+ * thread; no data-path collective, the caller's current device is restored.  Returns the first failing slice's
+ * code (message: mistra_kpp_last_error). */
+int mistra_kpp_integrate_multi(int mech, int64_t ncell, const double *rconst, const double *fix, double *var,
+                               double t0, double t1, const mistra_kpp_opts *o, int32_t *ierr, int32_t *stats,
+                               double *hexit, double *texit, int ndev, const int *devices);
+int mistra_kpp_device_count(void);
+
+/* Page-locked host memory.  mistra_kpp_integrate takes pageable arrays (Fortran COMMON / module arrays) as they
+ * are, but only page-locked ones let its chunk pipeline overlap the copies with the kernels: either allocate the
+ * batch arrays here, or register existing arrays once at start-up (e.g. the stacked RCONST / VAR arrays of the
+ * patched kpp_driver) and unregister them before they are freed. */
+int mistra_kpp_host_alloc(void **p, size_t bytes);
+int mistra_kpp_host_free(void *p);
+int mistra_kpp_host_register(void *p, size_t bytes);
+int mistra_kpp_host_unregister(void *p);
+
 int64_t mistra_kpp_launch_count(void);
 
 /* Kernel variant of a mechanism (a tuning knob, results agree within the parity contract):

@@ -30,6 +30,10 @@ void integrate_a_(double *tin, double *tout);
 /* replaces SUBROUTINE INTEGRATE_t(TIN,TOUT)  /root/reference/src/tot.f:2812 */
 void integrate_t_(double *tin, double *tout);
 
+/* Optional: hand the shim the address of a mechanism's COMMON /GDATA_x/ image (mech = 0 gas, 1 aer, 2 tot) instead
+ * of letting it look the symbol gdata_x_ up in the process (dlsym) at the first call. */
+void mistra_kpp_f77_bind(int mech, void *gdata);
+
 /* COMMON-block images the shims bind to (defined by the Fortran program). */
 struct mistra_gdata_g { double C[105], RCONST[331], TIME, DT, ATOL[102], RTOL[102], STEPMIN, STEPMAX; };
 struct mistra_gdata_a { double C[262], RCONST[979], TIME, DT, ATOL[257], RTOL[257], STEPMIN, STEPMAX; };

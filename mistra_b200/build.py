@@ -128,6 +128,7 @@ def build(verbose=False, strict=True, ptxas_v=False):
         outs.append(so)
     outs.append(build_rconst(verbose))
     outs.append(build_f77(verbose))
+    outs.append(build_b1_host(verbose))
     return outs
 
 
@@ -157,8 +158,29 @@ def build_f77(verbose=False):
     if os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == hv:
         return so
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
-    cmd = [cc, "-O2", "-fPIC", "-shared", "-o", so, src, "-L" + HERE, "-lmistra_kpp",
+    cmd = [cc, "-O2", "-fPIC", "-shared", "-o", so, src, "-L" + HERE, "-lmistra_kpp", "-ldl",
            "-Wl,-rpath,$ORIGIN"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    with open(stamp, "w") as f:
+        f.write(hv)
+    return so
+
+
+def build_b1_host(verbose=False):
+    """tests/host/libb1_host.so: a stand-in for the Fortran host of boundary B1 (defines the COMMON blocks, calls the
+    shims) - test / bench infrastructure, not part of the product."""
+    src = os.path.join(ROOT, "tests", "host", "b1_host.c")
+    so = os.path.join(ROOT, "tests", "host", "libb1_host.so")
+    deps = [src, os.path.join(ROOT, "include", "mistra_kpp_f77.h")]
+    hv = _hash(deps, HOSTCXX)
+    stamp = os.path.join(OBJ, "b1_host.sha")
+    if os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == hv:
+        return so
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    cmd = [cc, "-O2", "-fPIC", "-shared", "-o", so, src, "-L" + HERE, "-lmistra_kpp_f77",
+           "-Wl,-rpath," + HERE]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)

@@ -12,10 +12,12 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 namespace {
 
-std::mutex g_mu;
+std::mutex g_mu;                 // the device table, the kernel-variant choice
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 void *g_oc_aux = nullptr;      // development aid of the on-chip kernels (OC_DEBUG builds dump checkpoints here)
@@ -51,6 +53,8 @@ struct DeviceState {
 
 constexpr int kMaxDev = 16;
 DeviceState g_dev[kMaxDev];
+// one lock per device: host threads that drive different GPUs of one process run concurrently
+std::mutex g_dev_mu[kMaxDev];
 
 int fail(int code, const std::string &msg)
 {
@@ -367,10 +371,14 @@ int mistra_kpp_integrate_device(int mech, int64_t ncell, const double *d_rconst,
   if (ncell < 0) return fail(MISTRA_KPP_EINVAL, "ncell < 0");
   if (ncell > 0 && (!d_rconst || !d_fix || !d_var))
     return fail(MISTRA_KPP_EINVAL, "null rconst/fix/var");
-  std::lock_guard<std::mutex> lk(g_mu);
   DeviceState *d;
-  int rc = get_device(&d);
+  int rc;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    rc = get_device(&d);
+  }
   if (rc) return rc;
+  std::lock_guard<std::mutex> dl(g_dev_mu[d->dev]);
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream, as in the CUDA runtime
   // Experiment (MISTRA_KPP_SPLIT=1): the two halves of a long batch as two co-resident kernels.
   static const bool split = getenv("MISTRA_KPP_SPLIT") && atoi(getenv("MISTRA_KPP_SPLIT")) > 0;
@@ -408,10 +416,14 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
     int rc = decode_opts(o, t0, t1, &tmp);  // reject bad options before touching the device
     if (rc) return rc;
   }
-  std::lock_guard<std::mutex> lk(g_mu);
   DeviceState *d;
-  int rc = get_device(&d);
+  int rc;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    rc = get_device(&d);
+  }
   if (rc) return rc;
+  std::lock_guard<std::mutex> dl(g_dev_mu[d->dev]);
   cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
   if (ncell == 0) return 0;
 
@@ -460,6 +472,9 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
   CK(cudaStreamWaitEvent(d->s_h2d, d->ev_start, 0));
   CK(cudaStreamWaitEvent(d->s_d2h, d->ev_start, 0));
   CK(cudaStreamWaitEvent(d->s_k2, d->ev_start, 0));
+  // a failure in the middle of the pipeline must not leave copies in flight that still read or write the
+  // caller's arrays after the call has returned: the four streams are drained before the error is reported
+  auto pipeline = [&]() -> int {
   for (int64_t c = 0, off = 0; off < ncell; ++c, off += per) {
     const int slot = (int)(c & 1);
     cudaStream_t ks = slot ? d->s_k2 : st;
@@ -496,9 +511,107 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
   CK(cudaStreamSynchronize(d->s_d2h));
   CK(cudaStreamSynchronize(st));
   return 0;
+  };
+  rc = pipeline();
+  if (rc) {
+    const std::string msg = g_err;
+    cudaStreamSynchronize(d->s_h2d);
+    cudaStreamSynchronize(d->s_k2);
+    cudaStreamSynchronize(d->s_d2h);
+    cudaStreamSynchronize(st);
+    g_err = msg;
+  }
+  return rc;
 }
 
 int64_t mistra_kpp_launch_count(void) { return g_launches.load(); }
+
+// ---- page-locked host memory: what lets the chunk pipeline overlap its copies with the kernels ----------------
+int mistra_kpp_host_alloc(void **p, size_t bytes)
+{
+  if (!p) return fail(MISTRA_KPP_EINVAL, "null pointer");
+  *p = nullptr;
+  if (bytes == 0) return 0;
+  CK(cudaHostAlloc(p, bytes, cudaHostAllocPortable));
+  return 0;
+}
+
+int mistra_kpp_host_free(void *p)
+{
+  if (p) CK(cudaFreeHost(p));
+  return 0;
+}
+
+int mistra_kpp_host_register(void *p, size_t bytes)
+{
+  if (!p || bytes == 0) return fail(MISTRA_KPP_EINVAL, "null array");
+  CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+
+int mistra_kpp_host_unregister(void *p)
+{
+  if (!p) return fail(MISTRA_KPP_EINVAL, "null array");
+  CK(cudaHostUnregister(p));
+  return 0;
+}
+
+// ---- all GPUs of the box from one process ------------------------------------------------------------------
+int mistra_kpp_device_count(void)
+{
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  return n;
+}
+
+int mistra_kpp_integrate_multi(int mech, int64_t ncell, const double *rconst, const double *fix, double *var,
+                               double t0, double t1, const mistra_kpp_opts *o, int32_t *ierr, int32_t *stats,
+                               double *hexit, double *texit, int ndev, const int *devices)
+{
+  const KppMechInfo *mi = mech_info(mech);
+  if (!mi) return fail(MISTRA_KPP_EINVAL, "unknown mechanism id");
+  if (ncell < 0) return fail(MISTRA_KPP_EINVAL, "ncell < 0");
+  if (ncell > 0 && (!rconst || !fix || !var)) return fail(MISTRA_KPP_EINVAL, "null rconst/fix/var");
+  {
+    KppBatch tmp;
+    int rc = decode_opts(o, t0, t1, &tmp);
+    if (rc) return rc;
+  }
+  int visible = 0;
+  CK(cudaGetDeviceCount(&visible));
+  if (visible < 1) return fail(MISTRA_KPP_ENODEVICE, "no CUDA device");
+  if (ndev <= 0) { ndev = visible; devices = nullptr; }
+  if (ndev > 64) return fail(MISTRA_KPP_EINVAL, "more than 64 slices");
+  std::vector<int> devs(ndev);
+  for (int i = 0; i < ndev; ++i) {
+    devs[i] = devices ? devices[i] : i;
+    if (devs[i] < 0 || devs[i] >= visible || devs[i] >= kMaxDev) return fail(MISTRA_KPP_EINVAL, "device index out of range");
+  }
+  int cur = 0;
+  CK(cudaGetDevice(&cur));
+  // contiguous slices of cells, one host thread per slice (a device listed twice gets two slices, one after the other)
+  std::vector<int> rcs(ndev, 0);
+  std::vector<std::string> msgs(ndev);
+  auto work = [&](int i) {
+    const int64_t lo = ncell * i / ndev, hi = ncell * (i + 1) / ndev, m = hi - lo;
+    if (m <= 0) return;
+    cudaError_t e = cudaSetDevice(devs[i]);
+    if (e != cudaSuccess) { rcs[i] = cuda_fail(e, "cudaSetDevice"); msgs[i] = g_err; return; }
+    rcs[i] = mistra_kpp_integrate(mech, m, rconst + lo * mi->nreact, fix + lo * mi->nfix, var + lo * mi->nvar, t0, t1, o,
+                                  ierr ? ierr + lo : nullptr, stats ? stats + lo * 8 : nullptr,
+                                  hexit ? hexit + lo : nullptr, texit ? texit + lo : nullptr, nullptr);
+    if (rcs[i]) msgs[i] = g_err;
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < ndev; ++i) th.emplace_back(work, i);
+  work(0);
+  for (auto &t : th) t.join();
+  cudaSetDevice(cur);
+  for (int i = 0; i < ndev; ++i)
+    if (rcs[i]) { g_err = "slice " + std::to_string(i) + " (device " + std::to_string(devs[i]) + "): " + msgs[i]; return rcs[i]; }
+  return 0;
+}
 
 int mistra_kpp_set_kernel(int mech, int variant)
 {
@@ -530,6 +643,7 @@ int mistra_kpp_finalize(void)
   int cur = -1;
   cudaGetDevice(&cur);
   for (int i = 0; i < kMaxDev; ++i) {
+    std::lock_guard<std::mutex> dl(g_dev_mu[i]);
     DeviceState &d = g_dev[i];
     if (!d.init) continue;
     cudaSetDevice(i);

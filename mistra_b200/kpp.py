@@ -59,6 +59,12 @@ def library(strict=False):
                                            C.POINTER(KppOpts), ip, ip, dp, dp, vp]
         L.mistra_kpp_integrate_device.argtypes = [C.c_int, C.c_int64, vp, vp, vp, C.c_double,
                                                   C.c_double, C.POINTER(KppOpts), vp, vp, vp, vp, vp]
+        L.mistra_kpp_integrate_multi.argtypes = [C.c_int, C.c_int64, dp, dp, dp, C.c_double, C.c_double,
+                                                 C.POINTER(KppOpts), ip, ip, dp, dp, C.c_int, C.POINTER(C.c_int)]
+        L.mistra_kpp_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        L.mistra_kpp_host_free.argtypes = [C.c_void_p]
+        L.mistra_kpp_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        L.mistra_kpp_host_unregister.argtypes = [C.c_void_p]
         L.mistra_kpp_launch_count.restype = C.c_int64
         L.mistra_kpp_fp64_peak_tflops.restype = C.c_double
         L.mistra_kpp_last_error.restype = C.c_char_p
@@ -154,6 +160,70 @@ def integrate_device(mech, rconst, fix, var, t0=0.0, t1=10.0, opts=None, ierr=No
                                        C.byref(o), ptr(ierr), ptr(stats), ptr(hexit), ptr(texit),
                                        C.c_void_p(stream))
     _check(L, rc)
+
+
+def integrate_multi(mech, rconst, fix, var, t0=0.0, t1=10.0, opts=None, devices=None, strict=False):
+    """INTEGRATE_x for a batch of cells in HOST arrays over several GPUs of the box from this one process
+    (mistra_kpp_integrate_multi): contiguous slices of cells, slice i on CUDA device devices[i] (None: all visible).
+    Returns (var_out, ierr, stats, hexit, texit)."""
+    L = library(strict)
+    nvar, nfix, nreact, _ = query(mech, strict)
+    var_out = np.array(var, dtype=np.float64, order="C").reshape(-1, nvar)
+    ncell = var_out.shape[0]
+    rconst = np.ascontiguousarray(rconst, dtype=np.float64).reshape(ncell, nreact)
+    fix = np.ascontiguousarray(fix, dtype=np.float64).reshape(ncell, nfix)
+    ierr = np.zeros(ncell, dtype=np.int32)
+    stats = np.zeros((ncell, 8), dtype=np.int32)
+    hexit = np.zeros(ncell, dtype=np.float64)
+    texit = np.zeros(ncell, dtype=np.float64)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    o = opts if opts is not None else default_opts(strict)
+    if devices is None:
+        ndev, dv = 0, None
+    else:
+        ndev = len(devices)
+        dv = (C.c_int * ndev)(*devices)
+    rc = L.mistra_kpp_integrate_multi(mech, ncell, rconst.ctypes.data_as(dp), fix.ctypes.data_as(dp),
+                                      var_out.ctypes.data_as(dp), t0, t1, C.byref(o), ierr.ctypes.data_as(ip),
+                                      stats.ctypes.data_as(ip), hexit.ctypes.data_as(dp), texit.ctypes.data_as(dp),
+                                      ndev, dv)
+    _check(L, rc)
+    return var_out, ierr, stats, hexit, texit
+
+
+def device_count(strict=False):
+    return int(library(strict).mistra_kpp_device_count())
+
+
+class PinnedArray:
+    """A numpy array over page-locked host memory from mistra_kpp_host_alloc (freed with the object)."""
+
+    def __init__(self, shape, dtype=np.float64, strict=False):
+        self._L = library(strict)
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._p = C.c_void_p()
+        _check(self._L, self._L.mistra_kpp_host_alloc(C.byref(self._p), max(n, 1)))
+        buf = (C.c_char * max(n, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self._p:
+                self.array = None
+                self._L.mistra_kpp_host_free(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
+def host_register(a, strict=False):
+    L = library(strict)
+    _check(L, L.mistra_kpp_host_register(C.c_void_p(a.ctypes.data), a.nbytes))
+
+
+def host_unregister(a, strict=False):
+    L = library(strict)
+    _check(L, L.mistra_kpp_host_unregister(C.c_void_p(a.ctypes.data)))
 
 
 def set_kernel(mech, variant, strict=False):

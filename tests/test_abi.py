@@ -38,6 +38,24 @@ def test_library_exports_every_declared_symbol(kpp, header, lib):
         assert hasattr(L, n), "%s does not export %s" % (lib, n)
 
 
+def test_b1_shim_exports_the_fortran_entry_points(kpp):
+    """Boundary B1: lower-case names with a trailing underscore (gfortran / ifort), plus the optional bind call; the
+    library loads into a process without a Fortran host, and an unbound COMMON block is reported, not dereferenced."""
+    L = C.CDLL(os.path.join(ROOT, "mistra_b200", "libmistra_kpp_f77.so"))
+    for n in ("integrate_g_", "integrate_a_", "integrate_t_", "mistra_kpp_f77_bind"):
+        assert hasattr(L, n)
+    host = os.path.join(ROOT, "tests", "host", "libb1_host.so")
+    assert os.path.exists(host), "tests/host/libb1_host.so is built by mistra_b200.build"
+    H = C.CDLL(host, mode=C.RTLD_GLOBAL)
+    for n in ("gdata_g_", "gdata_a_", "gdata_t_", "b1_integrate", "b1_latency_us"):
+        assert hasattr(H, n)
+    for name, sym in (("gas", "gdata_g_"), ("aer", "gdata_a_"), ("tot", "gdata_t_")):
+        m = mechmod.load(name)
+        doubles = (m.nvar + m.nfix) + m.nreact + 2 + 2 * m.nvar + 2      # gas_Global.h:28-58
+        nxt = {"gdata_g_": 644, "gdata_a_": 1759, "gdata_t_": 2889}[sym]
+        assert doubles == nxt
+
+
 def test_query_and_species_names(kpp):
     for mi, name in enumerate(mechmod.MECH_NAMES):
         m = mechmod.load(name)
