@@ -49,6 +49,12 @@ def parse_args():
     ap.add_argument("--spinup", type=int, default=int(os.environ.get("MISTRA_BENCH_SPINUP", "12")))
     ap.add_argument("--cpu-sample-cols", type=int, default=200,
                     help="columns per step of the --impl reference arm")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --cols columns per GPU; strong: --cols columns in total, split over the GPUs")
+    ap.add_argument("--tot-cells", type=int, default=int(os.environ.get("MISTRA_BENCH_TOT_CELLS", "100000")),
+                    help="cloudy cells of the tot leg (SURVEY 8d: 1e5); 0 = skip")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the tot / cold-start / latency / on-chip / pageable legs (rank 0, N=1 only anyway)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bins", action="store_true", help="skip the 2-D particle-grid legs (bins, kon)")
@@ -219,6 +225,166 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ----------------------------------------------------------------------------
+def parity_check(dbatches, batches, ncheck=1000):
+    """A sample of the TIMED output (last timed step, device arm) against the CPU oracle on the same inputs:
+    parity contract of tests/test_gpu_parity.py (RTOL 1e-3 with an ATOL floor of 1e-3 molecule cm^-3, identical
+    ierr, share of cells on the oracle's accept/reject sequence)."""
+    from oracle import kpp_oracle as ko
+    out = {}
+    ok_all = True
+    for d, (mname, var, rc, fix) in zip(dbatches, batches):
+        n = var.shape[0]
+        idx = np.unique(np.linspace(0, n - 1, min(ncheck, n)).astype(np.int64))
+        ref, ierr_o, stats_o, _, _ = ko.integrate(MECH_ID[mname], rc[idx], fix[idx], var[idx],
+                                                  nthreads=os.cpu_count() or 1)
+        tidx = torch_index(idx, d["var0"].device)
+        got = d["vars"][-1][tidx].cpu().numpy()
+        ierr = d["ierr"][tidx].cpu().numpy()
+        stats = d["stats"][tidx].cpu().numpy()
+        good = (ierr == 1) & (ierr_o == 1)
+        rel = np.abs(got[good] - ref[good]) / (np.maximum(np.abs(got[good]), np.abs(ref[good])) + 1.66e-21)
+        same = (stats[:, 2:5] == stats_o[:, 2:5]).all(axis=1)
+        res = {"cells": int(len(idx)), "max_rel_err": float(rel.max()) if rel.size else 0.0,
+               "ierr_equal": bool(np.array_equal(ierr, ierr_o)), "same_step_sequence": float(same.mean()),
+               "ok": bool(np.array_equal(ierr, ierr_o) and (rel.size == 0 or rel.max() <= 1e-3))}
+        ok_all = ok_all and res["ok"]
+        out[mname] = res
+    out["ok"] = ok_all
+    out["note"] = ("last timed step of the device arm vs the CPU oracle (C restatement of the reference; parity "
+                   "unpinned by the reference, SURVEY 8c) on evenly spaced cells; tolerance RTOL 1e-3, floor 1.66e-21 mol m^-3")
+    return out
+
+
+def torch_index(idx, device):
+    import torch
+    return torch.from_numpy(idx).to(device)
+
+
+def time_device(kpp, torch, mech, d_rc, d_fix, d_var0, repeats=3):
+    """Median device time (CUDA events) of one INTEGRATE over a device-resident batch, state restored outside the clock."""
+    n = d_var0.shape[0]
+    ierr = torch.zeros(n, dtype=torch.int32, device=d_var0.device)
+    stats = torch.zeros((n, 8), dtype=torch.int32, device=d_var0.device)
+    work = d_var0.clone()
+    ts = []
+    for it in range(repeats + 1):
+        work.copy_(d_var0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        kpp.integrate_device(mech, d_rc, d_fix, work, ierr=ierr, stats=stats)
+        e1.record()
+        torch.cuda.synchronize()
+        if it:
+            ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), stats.cpu().numpy(), ierr.cpu().numpy(), work
+
+
+def run_extras(args, dev, batches, dbatches):
+    """Legs beside the headline (rank 0, one GPU): the tot mechanism, a cold-start batch with rejected steps, the
+    one-cell-per-call latency of the box-model configuration, the on-chip kernel variant, pageable host buffers."""
+    import ctypes as C
+    import torch
+    from mistra_b200 import kpp, synthetic
+    from mistra_b200.mechgen import mech as mechmod
+    fp64_peak = kpp.fp64_peak_tflops()
+    peaks, _ = measured_peaks()
+    res = {}
+
+    def roof(mname, stats, ms, ncell):
+        m = mechmod.load(mname)
+        flops = float(m.flops_from_stats(stats))
+        nstp = float(stats[:, 2].sum())
+        step_bytes = 8.0 * (8 * m.lu_nonzero + 40 * m.nvar + 4 * m.nreact)
+        return {"cells": int(ncell), "kernel_ms": ms, "cells_per_s": ncell / (ms * 1e-3), "ros3_steps_per_s": nstp / (ms * 1e-3),
+                "mean_steps_per_cell": nstp / max(1, ncell), "sum_nrej": float(stats[:, 4].sum()),
+                "fp64": {"achieved": flops / (ms * 1e-3) * 1e-12, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": flops / (ms * 1e-3) * 1e-12 / fp64_peak},
+                "hbm_stream": {"achieved": step_bytes * nstp / (ms * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                               "frac": step_bytes * nstp / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"]}}
+
+    # ---- tot: 1e5 cloudy cells (SURVEY 8d), spun up like the other batches ------------------------------------
+    if args.tot_cells > 0:
+        cols = max(1, args.tot_cells // synthetic.TotEnsemble.LAYERS)
+        _, var, rc, fix = build_ensemble("tot", cols, 0, args.spinup, use_gpu=True, chunk_cols=250)
+        ms, stats, ierr, _ = time_device(kpp, torch, 2, torch.from_numpy(rc).to(dev), torch.from_numpy(fix).to(dev),
+                                         torch.from_numpy(var).to(dev))
+        res["tot"] = roof("tot", stats, ms, var.shape[0])
+        res["tot"]["failed_cells"] = int((ierr != 1).sum())
+        res["tot"]["kernel"] = "ros3_kernel_t (cell per thread, workspace in HBM)"
+        del var, rc, fix
+        torch.cuda.empty_cache()
+
+    # ---- cold start: no spin-up, radicals at zero -> many steps per cell and rejected steps -----------------------
+    cold = {}
+    for mname, cols in (("gas", 400), ("aer", 400)):
+        _, var, rc, fix = build_ensemble(mname, cols, 0, 0, use_gpu=True)
+        ms, stats, ierr, _ = time_device(kpp, torch, MECH_ID[mname], torch.from_numpy(rc).to(dev),
+                                         torch.from_numpy(fix).to(dev), torch.from_numpy(var).to(dev), repeats=2)
+        cold[mname] = roof(mname, stats, ms, var.shape[0])
+        cold[mname]["failed_cells"] = int((ierr != 1).sum())
+    cold["note"] = ("first chemistry step of a cold ensemble (radicals start at zero, kpp.f90:283-287): step counts differ "
+                    "from cell to cell and steps are rejected, so lanes refill at different times")
+    res["cold_start"] = cold
+
+    # ---- on-chip kernel variant on the aer batch (first 98 000 cells) -------------------------------------------
+    da = [d for d in dbatches if d["name"] == "aer"]
+    if da:
+        d = da[0]
+        n = min(d["n"], 98000)
+        kpp.set_kernel(1, 1)
+        try:
+            ms, stats, ierr, _ = time_device(kpp, torch, 1, d["rc"][:n].contiguous(), d["fix"][:n].contiguous(),
+                                             d["var0"][:n].contiguous())
+        finally:
+            kpp.set_kernel(1, 0)
+        msd, statsd, _, _ = time_device(kpp, torch, 1, d["rc"][:n].contiguous(), d["fix"][:n].contiguous(),
+                                        d["var0"][:n].contiguous())
+        oc = roof("aer", stats, ms, n)
+        oc["kernel"] = "ros3_onchip_a (one persistent block per SM, 5 cell slots, LU in shared memory / registers)"
+        oc["default_kernel_same_cells"] = {"kernel_ms": msd, "cells_per_s": n / (msd * 1e-3)}
+        oc["dram_bytes_per_cell"] = {"value": 10.2e3, "compulsory": 11984,
+                                     "source": "ncu --set full capture profiles/r02_onchip_aer_ncu_full.txt (dram read+write / cells)"}
+        res["onchip_aer"] = oc
+
+    # ---- one cell per call: the box-model configuration namelist.Buys13_0D (kpp.f90:4296-4299) ----------------
+    lat = {}
+    host = os.path.join(ROOT, "tests", "host", "libb1_host.so")
+    H = C.CDLL(host, mode=C.RTLD_GLOBAL) if os.path.exists(host) else None
+    dp = C.POINTER(C.c_double)
+    if H is not None:
+        H.b1_latency_us.argtypes = [C.c_int, dp, dp, dp, C.c_int, C.c_int]
+        H.b1_latency_us.restype = C.c_double
+    for mname, var, rc, fix in batches:
+        v1, r1, f1 = (np.ascontiguousarray(a[:1]) for a in (var, rc, fix))
+        mech = MECH_ID[mname]
+        for _ in range(20):
+            kpp.integrate(mech, r1, f1, v1)
+        t0 = time.perf_counter()
+        ncall = 300
+        for _ in range(ncall):
+            kpp.integrate(mech, r1, f1, v1)
+        py_us = (time.perf_counter() - t0) / ncall * 1e6
+        ent = {"b2_python_us_per_call": py_us}
+        if H is not None:
+            H.b1_latency_us(mech, v1.ctypes.data_as(dp), f1.ctypes.data_as(dp), r1.ctypes.data_as(dp), 50, 1)
+            ent["b1_us_per_call"] = float(H.b1_latency_us(mech, v1.ctypes.data_as(dp), f1.ctypes.data_as(dp),
+                                                          r1.ctypes.data_as(dp), 1000, 1))
+        from oracle import kpp_oracle as ko
+        t0 = time.perf_counter()
+        for _ in range(50):
+            ko.integrate(mech, r1, f1, v1, nthreads=1)
+        ent["cpu_oracle_us_per_call"] = (time.perf_counter() - t0) / 50 * 1e6
+        lat[mname] = ent
+    lat["note"] = ("one spun-up cell per call, 0 -> 10 s: B1 = integrate_x_ of libmistra_kpp_f77.so called from C with the "
+                   "state in the COMMON blocks (tests/host/b1_host.c, 1000 calls), B2 = mistra_kpp_integrate through ctypes "
+                   "(includes the Python call overhead), CPU = the oracle on one thread; 8640 such calls make up Buys13_0D")
+    res["latency_1cell"] = lat
+    return res
+
+
 # ----------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -242,9 +408,12 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     mechs = args.mechs.split(",")
+    cols_rank = args.cols
+    if args.scaling == "strong":                       # the same --cols columns in total, whatever the GPU count
+        cols_rank = args.cols // world + (1 if rank < args.cols % world else 0)
     batches = []
     for mname in mechs:
-        ens, var, rc, fix = build_ensemble(mname, args.cols, rank, args.spinup, use_gpu=True)
+        ens, var, rc, fix = build_ensemble(mname, cols_rank, rank, args.spinup, use_gpu=True)
         batches.append((mname, var, rc, fix))
     ncell_rank = sum(b[1].shape[0] for b in batches)
 
@@ -265,28 +434,37 @@ def run_b200(args):
 
     kev = []  # (mech name, start event, end event) around each kernel launch of the timed steps
 
-    def step_device(timed):
+    # every timed step integrates its own copy of the saved state, made before the clock starts: the restore is
+    # the bench's bookkeeping, not part of the path
+    for d in dbatches:
+        d["vars"] = [d["var0"].clone() for _ in range(args.steps)]
+
+    def step_device(k):
         for d in dbatches:
-            d["var"].copy_(d["var0"])
+            if k < 0:
+                d["var"].copy_(d["var0"])
+                v = d["var"]
+            else:
+                v = d["vars"][k]
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            kpp.integrate_device(d["mech"], d["rc"], d["fix"], d["var"], 0.0, 10.0, ierr=d["ierr"],
+            kpp.integrate_device(d["mech"], d["rc"], d["fix"], v, 0.0, 10.0, ierr=d["ierr"],
                                  stats=d["stats"], hexit=d["hexit"])
             e1.record(stream)
-            if timed:
+            if k >= 0:
                 kev.append((d["name"], e0, e1))
 
     for _ in range(args.warmup):
-        step_device(False)
+        step_device(-1)
     barrier()
     l0 = kpp.launch_count()
     with ClockSampler(local) as clk:
         t_start = torch.cuda.Event(enable_timing=True)
         t_end = torch.cuda.Event(enable_timing=True)
         t_start.record(stream)
-        for _ in range(args.steps):
-            step_device(True)
+        for k in range(args.steps):
+            step_device(k)
         t_end.record(stream)
         barrier()
     launches = kpp.launch_count() - l0
@@ -295,7 +473,10 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_per_step = float(tmax.item()) / args.steps
-    total_cells = ncell_rank * world
+    tc = torch.tensor([float(ncell_rank)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+    total_cells = int(tc.item())
     value = total_cells / (ms_per_step * 1e-3)
 
     # diagnostics (the only collective on the path): sum of steps / rejects / failures
@@ -337,6 +518,8 @@ def run_b200(args):
         "frac": step_bytes * nstp_dom / (kms * 1e-3) * 1e-9 / peaks["hbm_gbs"], "peak_source": peak_src,
         "kernel_ms": kms, "ros3_steps_per_launch": nstp_dom, "bytes_per_ros3_step": step_bytes,
         "traffic": (ncu_step_bytes * nstp_dom) if ncu_step_bytes else None,
+        "traffic_source": "not measured in this run: dram read+write bytes per Ros3 step of the ncu --set full capture "
+                          "profiles/r01b_aer_ncu_full.txt (aer) / profiles/r01_gas_cellperthread_ncu_full.txt (gas) x the Ros3 steps of this launch",
         "note": "algorithmic bytes = (8*LU_NONZERO + 40*NVAR + 4*NREACT)*8 B per Ros3 step x steps of the launch "
                 "(workspace passes of the cell-per-thread mapping, SURVEY 8d); traffic = dram read+write per step "
                 "of the ncu --set full capture in profiles/ x steps of this launch",
@@ -392,7 +575,23 @@ def run_b200(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": total_cells / (float(tt.item()) / args.steps), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": float(tt.item()) / args.steps * 1e3}
+               "ms_per_step": float(tt.item()) / args.steps * 1e3, "host_buffers": "page-locked (pinned)"}
+        # the same call with PAGEABLE host arrays (what a Fortran caller has unless it registers its arrays with
+        # mistra_kpp_host_register): copies are staged by the driver and do not overlap the kernels
+        if world == 1 and not args.no_extras:
+            pg = [(mech, v0.numpy().copy(), r.numpy().copy(), f.numpy().copy()) for mech, v0, v, r, f, dg in hb]
+            dtp = []
+            for it in range(3):
+                work = [v0.copy() for _, v0, _, _ in pg]
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for (mech, v0, r, f), w in zip(pg, work):
+                    kpp.integrate(mech, r, f, w, out=w)
+                torch.cuda.synchronize()
+                dtp.append(time.perf_counter() - t0)
+            e2e["pageable"] = {"value": total_cells / min(dtp[1:]), "unit": UNIT, "ms_per_step": min(dtp[1:]) * 1e3,
+                               "note": "same call, plain numpy (pageable) arrays for rconst, fix, var and the diagnostics"}
+            del pg, work
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------
     cpu = None
@@ -412,6 +611,13 @@ def run_b200(args):
                "value_1thread": c_1 / t_1, "sample_1thread": "%d cells, %.1f s" % (c_1, t_1),
                "note": "C restatement of the reference Fortran (no Fortran compiler in the image)"}
 
+    parity = parity_check(dbatches, batches) if rank == 0 else None
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        for d in dbatches:
+            d["vars"] = d["vars"][-1:]                 # free the per-step copies
+        torch.cuda.empty_cache()
+        extras = run_extras(args, dev, batches, dbatches)
     bins_res = None
     kon_res = None
     next_res = None
@@ -425,16 +631,23 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "synthetic ensemble of independent Mistra columns (SURVEY 8d), "
-                                   "%d columns per GPU (148 gas cells, 98 aer / tot cells per column), mechanisms: %s; Ros3 0->10 s, "
-                                   "RTOL 1e-3 ATOL 1e-25 Hstart 1e-3" % (args.cols, "+".join(mechs)),
-                       "cells_per_gpu": ncell_rank, "columns_per_gpu": args.cols,
+                                   "%d columns %s (148 gas cells, 98 aer / tot cells per column), mechanisms: %s; Ros3 0->10 s, "
+                                   "RTOL 1e-3 ATOL 1e-25 Hstart 1e-3" % (args.cols, "per GPU" if args.scaling == "weak" else "in total", "+".join(mechs)),
+                       "cells_per_gpu": ncell_rank, "columns_per_gpu": cols_rank,
+                       "spinup": "%d chemistry steps of 10 s before the timed state is saved (SURVEY 8d asks for 60; the mean "
+                                 "Ros3 steps per cell and the share of rejected steps no longer change after ~10, DESIGN.md 7)" % args.spinup,
+                       "timed_region": "K INTEGRATE calls per mechanism, each on its own copy of the saved state (copies made before the clock starts)",
                        "parallelism": "cells sharded by column over %d GPU(s), no data-path collective" % world,
                        "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no explicit flush"
                              % (sum(d["rc"].numel() * 8 + d["var"].numel() * 8 for d in dbatches) * 1e-9)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+            "tot": extras.get("tot") if extras else None,
+            "cold_start": extras.get("cold_start") if extras else None,
+            "onchip_aer": extras.get("onchip_aer") if extras else None,
+            "latency_1cell": extras.get("latency_1cell") if extras else None,
             "diagnostics": {"sum_nstp": float(diag[0]), "sum_nrej": float(diag[1]),
                             "failed_cells": float(diag[2]), "cells": float(diag[3]),
                             "mean_steps_per_cell": float(diag[0] / max(1.0, float(diag[3])))},

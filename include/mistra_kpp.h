@@ -131,13 +131,20 @@ int mistra_kpp_host_unregister(void *p);
 int64_t mistra_kpp_launch_count(void);
 
 /* Kernel variant of a mechanism (a tuning knob, results agree within the parity contract):
- *   0  one cell per thread, per-lane workspace in HBM (csrc/ros3_kernel.inc) - the default, fastest on B200 today;
+ *   0  one cell per thread, per-lane workspace in HBM (csrc/ros3_kernel.inc): needs tens of thousands of cells to fill
+ *      the device, the fastest one for large batches;
  *   1  on-chip kernel (csrc/ros3_onchip.inc): one persistent block per SM, cell slots in lockstep, the sparse head of
- *      the LU factors in shared memory, the dense tail in registers, DRAM traffic = compulsory I/O.  gas and aer only.
- * Takes effect at the next integrate call (workspaces are re-allocated).  MISTRA_KPP_ONCHIP=1 in the environment
- * makes 1 the default where it exists.  Returns 0 or a negative MISTRA_KPP_E* code. */
+ *      the LU factors in shared memory, the dense tail in registers, DRAM traffic = compulsory I/O; keeps a few hundred
+ *      cells in flight, the faster one for small batches and for the one-cell-per-call box model.  gas and aer only;
+ *  -1  (default) chosen per call by the batch size (measured crossover, csrc/kpp_api.cu).
+ * mistra_kpp_set_kernel pins a variant for a mechanism (MISTRA_KPP_ONCHIP=0/1 in the environment: for all);
+ * mistra_kpp_get_kernel returns the pinned variant or -1, mistra_kpp_kernel_for the variant a batch of ncell cells
+ * would run on, mistra_kpp_launch_count_variant the launches of a variant so far.  Returns 0 / a value or a negative
+ * MISTRA_KPP_E* code. */
 int mistra_kpp_set_kernel(int mech, int variant);
 int mistra_kpp_get_kernel(int mech);
+int mistra_kpp_kernel_for(int mech, int64_t ncell);
+int64_t mistra_kpp_launch_count_variant(int variant);
 
 /* Release device workspaces, pinned staging buffers and the library stream. */
 int mistra_kpp_finalize(void);

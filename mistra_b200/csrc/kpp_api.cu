@@ -20,17 +20,23 @@ namespace {
 std::mutex g_mu;                 // the device table, the kernel-variant choice
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_launches_variant[2];
 void *g_oc_aux = nullptr;      // development aid of the on-chip kernels (OC_DEBUG builds dump checkpoints here)
 long long g_oc_flags = 0;
 
 struct MechState {
+  // variant 0: one cell per thread (ros3_kernel.inc)
   double *ws = nullptr;    // lane workspace of kernels on the caller's stream
   double *ws2 = nullptr;   // second workspace: odd chunks of the host-buffer pipeline (allocated on first use)
   size_t ws_bytes = 0;
   int blocks = 0;
-  int coef_variant = -1;  // -1 unset, 0 f64 literals, 1 f32 literals
-  bool onchip = false;    // one thread block per cell (ros3_onchip.inc) instead of one thread per cell
-  unsigned short *oc_tab = nullptr;   // device copy of the on-chip kernel's instruction streams
+  int coef_variant = -1;   // -1 unset, 0 f64 literals, 1 f32 literals
+  // variant 1: on-chip kernel (ros3_onchip.inc)
+  unsigned short *oc_tab = nullptr;   // device copy of the instruction streams
+  double *oc_ws = nullptr, *oc_ws2 = nullptr;   // strict build only: tail block of the LU factors per cell slot
+  size_t oc_ws_bytes = 0;
+  int oc_blocks = 0;
+  int oc_lit_variant = -1;
 };
 
 struct DeviceState {
@@ -51,6 +57,12 @@ struct DeviceState {
   cudaEvent_t ev_slot[2] = {};
 };
 
+#ifndef KPP_ONCHIP_MAX_CELLS_G
+#define KPP_ONCHIP_MAX_CELLS_G 8192
+#endif
+#ifndef KPP_ONCHIP_MAX_CELLS_A
+#define KPP_ONCHIP_MAX_CELLS_A 98304
+#endif
 constexpr int kMaxDev = 16;
 DeviceState g_dev[kMaxDev];
 // one lock per device: host threads that drive different GPUs of one process run concurrently
@@ -158,74 +170,77 @@ double literal_value(const char *lit, int f32)
   return f32 ? (double)strtof(lit, nullptr) : strtod(lit, nullptr);
 }
 
-// Kernel variant of a mechanism: 0 = one cell per thread with the lane workspace in HBM (ros3_kernel.inc, the
-// faster one on B200 today and the default), 1 = the on-chip kernel (ros3_onchip.inc: one persistent block per
-// SM, LU in shared memory / registers, DRAM traffic = the compulsory I/O).  Chosen per mechanism with
-// mistra_kpp_set_kernel(); MISTRA_KPP_ONCHIP=1 in the environment makes 1 the default where it exists.
-// Both are CUDA paths, there is no CPU path.
+// Kernel variant of a mechanism: 0 = one cell per thread with the lane workspace in HBM (ros3_kernel.inc), 1 = the
+// on-chip kernel (ros3_onchip.inc: one persistent block per SM, LU in shared memory / registers, DRAM traffic =
+// the compulsory I/O), -1 = by batch size (the default): the on-chip kernel keeps only a few hundred cells in
+// flight, so it is the faster one for small batches and for the one-cell-per-call box model, the cell-per-thread
+// kernel needs tens of thousands of cells to fill the device and is the faster one for large batches (measured
+// crossovers below, tools/variant_sweep.py).  mistra_kpp_set_kernel() pins a variant; MISTRA_KPP_ONCHIP=0/1 in the
+// environment does the same for every mechanism.  Both are CUDA paths, there is no CPU path.
 int g_variant[3] = {-1, -1, -1};
-bool want_onchip(const KppMechInfo *mi, int mech)
+const int64_t kOnchipMaxCells[3] = {KPP_ONCHIP_MAX_CELLS_G, KPP_ONCHIP_MAX_CELLS_A, 0};
+bool want_onchip(const KppMechInfo *mi, int mech, int64_t ncell)
 {
   if (!mi->oc) return false;
-  if (g_variant[mech] >= 0) return g_variant[mech] == 1;
-  const char *e = getenv("MISTRA_KPP_ONCHIP");
-  return e && atoi(e) == 1;
+  int v = g_variant[mech];
+  if (v < 0) {
+    const char *e = getenv("MISTRA_KPP_ONCHIP");
+    if (e && (atoi(e) == 0 || atoi(e) == 1)) v = atoi(e);
+  }
+  if (v >= 0) return v == 1;
+  return ncell <= kOnchipMaxCells[mech];
 }
-
-int ensure_mech(DeviceState &d, int mech, const KppMechInfo *mi, int f32, cudaStream_t st)
+int ensure_mech(DeviceState &d, int mech, const KppMechInfo *mi, int f32, cudaStream_t st, bool onchip)
 {
   MechState &ms = d.mech[mech];
-  if ((ms.ws || ms.oc_tab) && ms.onchip != want_onchip(mi, mech)) {   // the variant was switched: start over
-    CK(cudaDeviceSynchronize());
-    if (ms.ws) cudaFree(ms.ws);
-    if (ms.ws2) cudaFree(ms.ws2);
-    if (ms.oc_tab) cudaFree(ms.oc_tab);
-    ms = MechState();
-  }
-  if (!ms.ws && !ms.oc_tab) {
-    ms.onchip = want_onchip(mi, mech);
-    int per_sm = 0;
-    if (ms.onchip) {
+  if (onchip) {
+    if (!ms.oc_tab) {
+      int per_sm = 0;
       CK(cudaFuncSetAttribute(mi->oc->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mi->oc->smem_bytes));
       CK(cudaFuncSetAttribute(mi->oc->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mi->oc->kernel, mi->oc->threads, mi->oc->smem_bytes));
-      if (per_sm > 1) per_sm = 1;   // one persistent block per SM
-    } else {
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mi->kernel, KPP_BLOCK, 0));
+      if (per_sm < 1) return fail(MISTRA_KPP_ECUDA, "on-chip kernel does not fit on an SM");
+      ms.oc_blocks = d.num_sm;      // one persistent block per SM
+      CK(cudaMalloc(&ms.oc_tab, mi->oc->table_count * sizeof(unsigned short)));
+      CK(cudaMemcpyAsync(ms.oc_tab, mi->oc->tables, mi->oc->table_count * sizeof(unsigned short),
+                         cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+#ifdef KPP_STRICT
+      // strict build: the tail block of the LU factors is also written out, for the reference-order
+      // backward substitution
+      ms.oc_ws_bytes = (size_t)ms.oc_blocks * mi->oc->slots * mi->oc->tail * mi->oc->tail * sizeof(double);
+      CK(cudaMalloc(&ms.oc_ws, ms.oc_ws_bytes));
+#endif
     }
+    if (ms.oc_lit_variant != f32) {
+      double h[64];
+      if (mi->oc->nlit > 64) return fail(MISTRA_KPP_EINVAL, "coefficient table too large");
+      for (int i = 0; i < mi->oc->nlit; ++i) h[i] = literal_value(mi->oc->literals[i], f32);
+      CK(cudaDeviceSynchronize());    // kernels that still read the previous table
+      CK(mi->oc->set_lit(h, st));
+      CK(cudaStreamSynchronize(st));  // h is on the stack
+      ms.oc_lit_variant = f32;
+    }
+    return 0;
+  }
+  if (!ms.ws) {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mi->kernel, KPP_BLOCK, 0));
     if (per_sm < 1) return fail(MISTRA_KPP_ECUDA, "kernel does not fit on an SM");
     if (const char *e = getenv("MISTRA_KPP_BLOCKS_PER_SM")) {
       int v = atoi(e);
       if (v >= 1 && v < per_sm) per_sm = v;
     }
     ms.blocks = per_sm * d.num_sm;
-    if (ms.onchip) {
-      CK(cudaMalloc(&ms.oc_tab, mi->oc->table_count * sizeof(unsigned short)));
-      CK(cudaMemcpyAsync(ms.oc_tab, mi->oc->tables, mi->oc->table_count * sizeof(unsigned short),
-                         cudaMemcpyHostToDevice, st));
-#ifdef KPP_STRICT
-      // strict build: the tail block of the LU factors is also written out, for the reference-order
-      // backward substitution
-      ms.ws_bytes = (size_t)ms.blocks * mi->oc->slots * mi->oc->tail * mi->oc->tail * sizeof(double);
-      CK(cudaMalloc(&ms.ws, ms.ws_bytes));
-#endif
-    } else {
-      const size_t warps = (size_t)ms.blocks * (KPP_BLOCK / 32);
-      ms.ws_bytes = warps * (size_t)mi->nslot * 32 * sizeof(double);
-      CK(cudaMalloc(&ms.ws, ms.ws_bytes));
-    }
+    const size_t warps = (size_t)ms.blocks * (KPP_BLOCK / 32);
+    ms.ws_bytes = warps * (size_t)mi->nslot * 32 * sizeof(double);
+    CK(cudaMalloc(&ms.ws, ms.ws_bytes));
   }
   if (ms.coef_variant != f32) {
     double h[64];
-    if (ms.onchip) {
-      if (mi->oc->nlit > 64) return fail(MISTRA_KPP_EINVAL, "coefficient table too large");
-      for (int i = 0; i < mi->oc->nlit; ++i) h[i] = literal_value(mi->oc->literals[i], f32);
-      CK(mi->oc->set_lit(h, st));
-    } else {
-      if (mi->ncoef > 64) return fail(MISTRA_KPP_EINVAL, "coefficient table too large");
-      for (int i = 0; i < mi->ncoef; ++i) h[i] = literal_value(mi->coef_literals[i], f32);
-      CK(mi->set_coef(h, st));
-    }
+    if (mi->ncoef > 64) return fail(MISTRA_KPP_EINVAL, "coefficient table too large");
+    for (int i = 0; i < mi->ncoef; ++i) h[i] = literal_value(mi->coef_literals[i], f32);
+    CK(mi->set_coef(h, st));
     CK(cudaStreamSynchronize(st));  // h is on the stack
     ms.coef_variant = f32;
   }
@@ -235,7 +250,7 @@ int ensure_mech(DeviceState &d, int mech, const KppMechInfo *mi, int f32, cudaSt
 int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rconst,
                   const double *d_fix, double *d_var, double t0, double t1,
                   const mistra_kpp_opts *o, int32_t *d_ierr, int32_t *d_stats, double *d_hexit,
-                  double *d_texit, cudaStream_t st, int slot = 0)
+                  double *d_texit, cudaStream_t st, int slot, bool onchip)
 {
   const KppMechInfo *mi = mech_info(mech);
   KppBatch b;
@@ -243,7 +258,7 @@ int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rcons
   int rc = decode_opts(o, t0, t1, &b);
   if (rc) return rc;
   const int f32 = o ? (o->f32_literals ? 1 : 0) : 1;
-  if ((rc = ensure_mech(d, mech, mi, f32, st))) return rc;
+  if ((rc = ensure_mech(d, mech, mi, f32, st, onchip))) return rc;
   if (ncell == 0) return 0;
   MechState &ms = d.mech[mech];
   b.rconst = d_rconst;
@@ -254,17 +269,22 @@ int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rcons
   b.hexit = d_hexit;
   b.texit = d_texit;
   b.ncell = ncell;
-  if (slot == 1 && !ms.ws2 && ms.ws_bytes) CK(cudaMalloc(&ms.ws2, ms.ws_bytes));
-  b.ws = slot ? ms.ws2 : ms.ws;
+  if (onchip) {
+    if (slot == 1 && !ms.oc_ws2 && ms.oc_ws_bytes) CK(cudaMalloc(&ms.oc_ws2, ms.oc_ws_bytes));
+    b.ws = slot ? ms.oc_ws2 : ms.oc_ws;
+  } else {
+    if (slot == 1 && !ms.ws2 && ms.ws_bytes) CK(cudaMalloc(&ms.ws2, ms.ws_bytes));
+    b.ws = slot ? ms.ws2 : ms.ws;
+  }
   b.oc_tab = ms.oc_tab;
   b.oc_aux = g_oc_aux;
   b.oc_flags = g_oc_flags;
   b.counter = d.counter + slot;
   CK(cudaStreamWaitEvent(st, d.ev_slot[slot], 0));
   CK(cudaMemsetAsync(b.counter, 0, sizeof(unsigned long long), st));
-  if (ms.onchip) {
+  if (onchip) {
     const long long need = (ncell + mi->oc->slots - 1) / mi->oc->slots;
-    int blocks = (int)(need < ms.blocks ? need : ms.blocks);
+    int blocks = (int)(need < ms.oc_blocks ? need : ms.oc_blocks);
     CK(mi->oc->launch(b, blocks, st));
   } else {
     long long need_blocks = (ncell + KPP_BLOCK - 1) / KPP_BLOCK;
@@ -273,6 +293,7 @@ int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rcons
   }
   CK(cudaEventRecord(d.ev_slot[slot], st));
   g_launches.fetch_add(1);
+  g_launches_variant[onchip ? 1 : 0].fetch_add(1);
   return 0;
 }
 
@@ -382,24 +403,25 @@ int mistra_kpp_integrate_device(int mech, int64_t ncell, const double *d_rconst,
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream, as in the CUDA runtime
   // Experiment (MISTRA_KPP_SPLIT=1): the two halves of a long batch as two co-resident kernels.
   static const bool split = getenv("MISTRA_KPP_SPLIT") && atoi(getenv("MISTRA_KPP_SPLIT")) > 0;
-  if (split && !want_onchip(mech_info(mech), mech) && ncell >= 8LL * d->num_sm * 2 * KPP_BLOCK) {
+  const bool oc = want_onchip(mech_info(mech), mech, ncell);
+  if (split && !oc && ncell >= 8LL * d->num_sm * 2 * KPP_BLOCK) {
     const KppMechInfo *mi = mech_info(mech);
     if ((rc = ensure_streams(d))) return rc;
     const int64_t h = ncell / 2;
     CK(cudaEventRecord(d->ev_start, st));
     CK(cudaStreamWaitEvent(d->s_k2, d->ev_start, 0));
-    if ((rc = launch_device(*d, mech, h, d_rconst, d_fix, d_var, t0, t1, o, d_ierr, d_stats, d_hexit, d_texit, st, 0)))
+    if ((rc = launch_device(*d, mech, h, d_rconst, d_fix, d_var, t0, t1, o, d_ierr, d_stats, d_hexit, d_texit, st, 0, false)))
       return rc;
     if ((rc = launch_device(*d, mech, ncell - h, d_rconst + h * mi->nreact, d_fix + h * mi->nfix, d_var + h * mi->nvar,
                             t0, t1, o, d_ierr ? d_ierr + h : nullptr, d_stats ? d_stats + 8 * h : nullptr,
-                            d_hexit ? d_hexit + h : nullptr, d_texit ? d_texit + h : nullptr, d->s_k2, 1)))
+                            d_hexit ? d_hexit + h : nullptr, d_texit ? d_texit + h : nullptr, d->s_k2, 1, false)))
       return rc;
     CK(cudaEventRecord(d->ev_join, d->s_k2));
     CK(cudaStreamWaitEvent(st, d->ev_join, 0));
     return 0;
   }
   return launch_device(*d, mech, ncell, d_rconst, d_fix, d_var, t0, t1, o, d_ierr, d_stats,
-                       d_hexit, d_texit, st);
+                       d_hexit, d_texit, st, 0, oc);
 }
 
 int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const double *fix,
@@ -456,8 +478,9 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
   // instead of waiting for its slowest cell (a drained grid per chunk cost ~25 % end to end).
   // Host buffers may be pageable (Fortran arrays) or pinned; cudaMemcpyAsync handles
   // both, only pinned ones actually overlap.
-  if ((rc = ensure_mech(*d, mech, mi, o ? (o->f32_literals ? 1 : 0) : 1, st))) return rc;
-  const int64_t resident = (int64_t)d->mech[mech].blocks * (d->mech[mech].onchip ? mi->oc->slots : KPP_BLOCK);
+  const bool oc = want_onchip(mi, mech, ncell);     // by the size of the whole batch, not of a chunk
+  if ((rc = ensure_mech(*d, mech, mi, o ? (o->f32_literals ? 1 : 0) : 1, st, oc))) return rc;
+  const int64_t resident = oc ? (int64_t)d->mech[mech].oc_blocks * mi->oc->slots : (int64_t)d->mech[mech].blocks * KPP_BLOCK;
   int64_t nchunk = ncell / (2 * resident);
   if (nchunk < 1) nchunk = 1;
   if (nchunk > 16) nchunk = 16;
@@ -490,7 +513,7 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
     rc = launch_device(*d, mech, (int64_t)m, d_rc + o0 * mi->nreact, d_fx + o0 * mi->nfix,
                        d_vr + o0 * mi->nvar, t0, t1, o, ierr ? d_ie + o0 : nullptr,
                        stats ? d_st + o0 * 8 : nullptr, hexit ? d_hx + o0 : nullptr,
-                       texit ? d_tx + o0 : nullptr, ks, slot);
+                       texit ? d_tx + o0 : nullptr, ks, slot, oc);
     if (rc) return rc;
     CK(cudaEventRecord(d->ev_k[c], ks));
   }
@@ -616,7 +639,7 @@ int mistra_kpp_integrate_multi(int mech, int64_t ncell, const double *rconst, co
 int mistra_kpp_set_kernel(int mech, int variant)
 {
   if (mech < 0 || mech > 2) return fail(MISTRA_KPP_EINVAL, "mech must be 0, 1 or 2");
-  if (variant < 0 || variant > 1) return fail(MISTRA_KPP_EINVAL, "variant must be 0 (cell per thread) or 1 (on-chip)");
+  if (variant < -1 || variant > 1) return fail(MISTRA_KPP_EINVAL, "variant must be -1 (by batch size), 0 (cell per thread) or 1 (on-chip)");
   if (variant == 1 && !mech_info(mech)->oc) return fail(MISTRA_KPP_EINVAL, "this mechanism has no on-chip kernel");
   std::lock_guard<std::mutex> lk(g_mu);
   g_variant[mech] = variant;
@@ -626,7 +649,18 @@ int mistra_kpp_set_kernel(int mech, int variant)
 int mistra_kpp_get_kernel(int mech)
 {
   if (mech < 0 || mech > 2) return fail(MISTRA_KPP_EINVAL, "mech must be 0, 1 or 2");
-  return want_onchip(mech_info(mech), mech) ? 1 : 0;
+  return g_variant[mech];
+}
+
+int mistra_kpp_kernel_for(int mech, int64_t ncell)
+{
+  if (mech < 0 || mech > 2) return fail(MISTRA_KPP_EINVAL, "mech must be 0, 1 or 2");
+  return want_onchip(mech_info(mech), mech, ncell) ? 1 : 0;
+}
+
+int64_t mistra_kpp_launch_count_variant(int variant)
+{
+  return (variant == 0 || variant == 1) ? g_launches_variant[variant].load() : -1;
 }
 
 // Internal (not part of include/mistra_kpp.h): hands a device buffer and a flag word to the on-chip kernels;
@@ -652,6 +686,8 @@ int mistra_kpp_finalize(void)
       if (m.ws) cudaFree(m.ws);
       if (m.ws2) cudaFree(m.ws2);
       if (m.oc_tab) cudaFree(m.oc_tab);
+      if (m.oc_ws) cudaFree(m.oc_ws);
+      if (m.oc_ws2) cudaFree(m.oc_ws2);
       m = MechState();
     }
     if (d.counter) cudaFree(d.counter);

@@ -227,13 +227,26 @@ def host_unregister(a, strict=False):
 
 
 def set_kernel(mech, variant, strict=False):
-    """Kernel variant of a mechanism: 0 = one cell per thread (default), 1 = on-chip (gas, aer)."""
+    """Kernel variant of a mechanism: -1 = by batch size (default), 0 = one cell per thread, 1 = on-chip (gas, aer)."""
     L = library(strict)
     _check(L, L.mistra_kpp_set_kernel(mech, variant))
 
 
 def get_kernel(mech, strict=False):
+    """Pinned variant of a mechanism, -1 = chosen per call by the batch size."""
     return int(library(strict).mistra_kpp_get_kernel(mech))
+
+
+def kernel_for(mech, ncell, strict=False):
+    L = library(strict)
+    L.mistra_kpp_kernel_for.argtypes = [C.c_int, C.c_int64]
+    return int(L.mistra_kpp_kernel_for(mech, ncell))
+
+
+def launch_count_variant(variant, strict=False):
+    L = library(strict)
+    L.mistra_kpp_launch_count_variant.restype = C.c_int64
+    return int(L.mistra_kpp_launch_count_variant(variant))
 
 
 def launch_count(strict=False):

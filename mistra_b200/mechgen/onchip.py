@@ -532,8 +532,7 @@ class Plan:
     # CPU emulation (numpy, IEEE double, no fused multiply-add): same order as the kernel
     # =============================================================================================
     def new_smem(self):
-        S = np.full(self.smem_doubles, np.nan)
-        S[self.ZERO] = 0.0
+        S = np.zeros(self.smem_doubles)          # the kernel zero-fills every slot before its first cell
         return S
 
     def emu_set_consts(self, S, fix, f32):
@@ -714,6 +713,12 @@ class Plan:
                         e = int(ws[i + 2 + k])
                         if e & 1:
                             acc[t] = acc[t] - S[gp[t] + k] * S[xb + (e >> 3)]
+                        elif h0 & (F_BEGIN | F_STORE) or (h0 >> 3):
+                            # the kernel has no branch here: a padded entry multiplies whatever follows the row in G
+                            # by the zero slot behind the vector - that operand must be a finite number
+                            assert (e >> 3) == self.n and S[xb + self.n] == 0.0
+                            assert np.isfinite(S[gp[t] + k]), "padded entry reads a non-finite operand"
+                            acc[t] = acc[t] - S[gp[t] + k] * S[xb + self.n]
                     gp[t] += NENT
                     if h0 & F_STORE:
                         v = acc[t]
@@ -756,6 +761,7 @@ class Plan:
         def A(r, c):
             return (32 * (c // 32) + (r % 32), r // 32, c % 32)
         S[xpb:xpb + T] = 0.0
+        S[xb + self.n] = 0.0                     # the zero slot behind the vector (kernel: set with the right-hand side)
         self.emu_frames(self.fwd_stream, self.fwd_nchunk, S, xb, xpb)
         X = S[xb:xb + self.n]
         for r in range(T):

@@ -28,6 +28,12 @@ def kpp():
         from mistra_b200 import build
         build.build(strict=True)
     k.library()
+    # The default picks the kernel variant by batch size (on-chip for small batches).  The parity suites pin the
+    # cell-per-thread kernels so that every module tests one thing; the on-chip variant and the choice by batch
+    # size have their own module (tests/test_gpu_zz_onchip.py, which switches and restores the setting).
+    for strict in (False, True):
+        for mech in (0, 1, 2):
+            k.set_kernel(mech, 0, strict=strict)
     return k
 
 

@@ -30,7 +30,24 @@ def onchip(kpp, cuda_device):
 def test_tot_has_no_onchip_kernel(kpp, cuda_device):
     with pytest.raises(kpp.KppError):
         kpp.set_kernel(2, 1)
-    assert kpp.get_kernel(2) == 0
+    assert kpp.kernel_for(2, 1) == 0
+
+
+def test_variant_by_batch_size(kpp, cuda_device):
+    """Default: one cell (the box model) and small batches run on-chip, large batches on the cell-per-thread kernel."""
+    for mech in (0, 1):
+        kpp.set_kernel(mech, -1)
+    try:
+        assert kpp.get_kernel(1) == -1
+        assert kpp.kernel_for(1, 1) == 1 and kpp.kernel_for(1, 10 ** 6) == 0
+        assert kpp.kernel_for(0, 1) == 1 and kpp.kernel_for(0, 10 ** 6) == 0
+        var, fix, rc = util.random_cells("aer", 40, 3)
+        n1 = kpp.launch_count_variant(1)
+        kpp.integrate(1, rc, fix, var)
+        assert kpp.launch_count_variant(1) == n1 + 1
+    finally:
+        for mech in (0, 1):
+            kpp.set_kernel(mech, 0)
 
 
 @pytest.mark.parametrize("name", ["gas_cells", "aer_cells"])
@@ -112,9 +129,10 @@ def test_same_results_as_the_default_kernel(kpp, cuda_device):
     for _ in range(2):
         var = kpp.integrate(1, ens.rconst(var), ens.fix, var)[0]
     rc = ens.rconst(var)
-    a, ierr_a, st_a, _, _ = kpp.integrate(1, rc, ens.fix, var)
-    kpp.set_kernel(1, 1)
+    kpp.set_kernel(1, 0)
     try:
+        a, ierr_a, st_a, _, _ = kpp.integrate(1, rc, ens.fix, var)
+        kpp.set_kernel(1, 1)
         b, ierr_b, st_b, _, _ = kpp.integrate(1, rc, ens.fix, var)
     finally:
         kpp.set_kernel(1, 0)
