@@ -46,7 +46,7 @@ def test_b1_shim_exports_the_fortran_entry_points(kpp):
         assert hasattr(L, n)
     host = os.path.join(ROOT, "tests", "host", "libb1_host.so")
     assert os.path.exists(host), "tests/host/libb1_host.so is built by mistra_b200.build"
-    H = C.CDLL(host, mode=C.RTLD_GLOBAL)
+    H = C.CDLL(host)      # local scope: a global load would let the product library's symbols interpose other test harnesses
     for n in ("gdata_g_", "gdata_a_", "gdata_t_", "b1_integrate", "b1_latency_us"):
         assert hasattr(H, n)
     for name, sym in (("gas", "gdata_g_"), ("aer", "gdata_a_"), ("tot", "gdata_t_")):
