@@ -127,7 +127,7 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------
-def build_ensemble(mech, cols, rank, spinup, use_gpu, chunk_cols=500):
+def build_ensemble(mech, cols, rank, spinup, use_gpu, chunk_cols=500, want_rates=False):
     """Synthetic per-rank ensemble, spun up so that the timed step sees a stiff
     quasi-steady radical state.  Built in chunks of columns (the per-species input
     arrays of the aqueous mechanism are large).  Spin-up uses the CUDA path when a
@@ -146,7 +146,7 @@ def build_ensemble(mech, cols, rank, spinup, use_gpu, chunk_cols=500):
 
         def step(rc, fix, var):
             return ko.integrate(MECH_ID[mech], rc, fix, var, nthreads=os.cpu_count() or 1)[0]
-    vs, rs, fs = [], [], []
+    vs, rs, fs, crs = [], [], [], []
     for c0 in range(0, cols, chunk_cols):
         nc = min(chunk_cols, cols - c0)
         ens = cls(nc, col0=rank * cols + c0)
@@ -159,7 +159,9 @@ def build_ensemble(mech, cols, rank, spinup, use_gpu, chunk_cols=500):
         if spinup > 0:
             rc = ens.rconst(var)
         vs.append(var); rs.append(rc); fs.append(ens.fix)
-    return None, np.ascontiguousarray(np.concatenate(vs)), np.ascontiguousarray(np.concatenate(rs)), \
+        if want_rates:
+            crs.append(ens.compact_rates(idx=crs[0].idx if crs else None))
+    return crs if want_rates else None, np.ascontiguousarray(np.concatenate(vs)), np.ascontiguousarray(np.concatenate(rs)), \
         np.ascontiguousarray(np.concatenate(fs))
 
 
@@ -338,13 +340,14 @@ def run_extras(args, dev, batches, dbatches):
         try:
             ms, stats, ierr, _ = time_device(kpp, torch, 1, d["rc"][:n].contiguous(), d["fix"][:n].contiguous(),
                                              d["var0"][:n].contiguous())
-        finally:
             kpp.set_kernel(1, 0)
-        msd, statsd, _, _ = time_device(kpp, torch, 1, d["rc"][:n].contiguous(), d["fix"][:n].contiguous(),
-                                        d["var0"][:n].contiguous())
+            msd, statsd, _, _ = time_device(kpp, torch, 1, d["rc"][:n].contiguous(), d["fix"][:n].contiguous(),
+                                            d["var0"][:n].contiguous())
+        finally:
+            kpp.set_kernel(1, -1)                      # back to the choice by batch size
         oc = roof("aer", stats, ms, n)
         oc["kernel"] = "ros3_onchip_a (one persistent block per SM, 5 cell slots, LU in shared memory / registers)"
-        oc["default_kernel_same_cells"] = {"kernel_ms": msd, "cells_per_s": n / (msd * 1e-3)}
+        oc["cell_per_thread_kernel_same_cells"] = {"kernel_ms": msd, "cells_per_s": n / (msd * 1e-3)}
         oc["dram_bytes_per_cell"] = {"value": 10.2e3, "compulsory": 11984,
                                      "source": "ncu --set full capture profiles/r02_onchip_aer_ncu_full.txt (dram read+write / cells)"}
         res["onchip_aer"] = oc
@@ -377,6 +380,7 @@ def run_extras(args, dev, batches, dbatches):
         for _ in range(50):
             ko.integrate(mech, r1, f1, v1, nthreads=1)
         ent["cpu_oracle_us_per_call"] = (time.perf_counter() - t0) / 50 * 1e6
+        ent["kernel_variant"] = "on-chip" if kpp.kernel_for(mech, 1) == 1 else "cell per thread"
         lat[mname] = ent
     lat["note"] = ("one spun-up cell per call, 0 -> 10 s: B1 = integrate_x_ of libmistra_kpp_f77.so called from C with the "
                    "state in the COMMON blocks (tests/host/b1_host.c, 1000 calls), B2 = mistra_kpp_integrate through ctypes "
@@ -412,8 +416,10 @@ def run_b200(args):
     if args.scaling == "strong":                       # the same --cols columns in total, whatever the GPU count
         cols_rank = args.cols // world + (1 if rank < args.cols % world else 0)
     batches = []
+    rate_parts = {}
     for mname in mechs:
-        ens, var, rc, fix = build_ensemble(mname, cols_rank, rank, args.spinup, use_gpu=True)
+        crs, var, rc, fix = build_ensemble(mname, cols_rank, rank, args.spinup, use_gpu=True, want_rates=not args.no_e2e)
+        rate_parts[mname] = crs
         batches.append((mname, var, rc, fix))
     ncell_rank = sum(b[1].shape[0] for b in batches)
 
@@ -548,34 +554,54 @@ def run_b200(args):
         h2d = sum(v0.numel() * 8 + r.numel() * 8 + f.numel() * 8 for _, v0, _, r, f, _ in hb)
         d2h = sum(v0.numel() * 8 + v0.shape[0] * (4 + 32 + 8 + 8) for _, v0, _, r, f, _ in hb)
 
-        def step_host():
+        def step_host(use_rates):
             # every buffer is pinned host memory; the saved state is restored outside the clock
             # (it is the bench's bookkeeping, not part of the path), the call itself moves
-            # rconst, fix, var to the device and var, ierr, stats, hexit, texit back
+            # its inputs to the device and var, ierr, stats, hexit, texit back
             for mech, v0, v, r, f, dg in hb:
                 v.copy_(v0)
             torch.cuda.synchronize()
             barrier()
             t0 = time.perf_counter()
             acc = 0
-            for mech, v0, v, r, f, dg in hb:
+            moved = 0
+            for (mech, v0, v, r, f, dg), cr in zip(hb, crp):
                 vn = v.numpy()
-                _, ierr, stats, hexit, _tx = kpp.integrate(mech, r.numpy(), f.numpy(), vn, out=vn,
-                                                           diag=tuple(t.numpy() for t in dg))
+                if use_rates:
+                    _, ierr, stats, hexit, _tx, mv = kpp.integrate_rates(mech, cr, f.numpy(), vn, out=vn,
+                                                                        diag=tuple(t.numpy() for t in dg))
+                    moved += mv
+                else:
+                    _, ierr, stats, hexit, _tx = kpp.integrate(mech, r.numpy(), f.numpy(), vn, out=vn,
+                                                               diag=tuple(t.numpy() for t in dg))
                 acc += int((ierr != 1).sum())
             torch.cuda.synchronize()
-            return time.perf_counter() - t0
-        for _ in range(max(1, args.warmup - 1)):
-            step_host()
-        dt = 0.0
-        for _ in range(args.steps):
-            dt += step_host()
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": total_cells / (float(tt.item()) / args.steps), "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": float(tt.item()) / args.steps * 1e3, "host_buffers": "page-locked (pinned)"}
+            return time.perf_counter() - t0, moved
+
+        def pinned(shape, dtype):
+            return torch.empty(tuple(shape), dtype=torch.float64).pin_memory().numpy()
+        crp = [kpp.CompactRates.concat(rate_parts[mname], alloc=pinned) for mname, _, _, _ in batches]
+        rate_parts.clear()
+        res = {}
+        for use_rates in (False, True):
+            for _ in range(max(1, args.warmup - 1)):
+                step_host(use_rates)
+            dt, moved = 0.0, 0
+            for _ in range(args.steps):
+                a, moved = step_host(use_rates)
+                dt += a
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            res[use_rates] = (float(tt.item()) / args.steps, moved)
+        e2e = {"value": total_cells / res[True][0], "unit": UNIT,
+               "h2d_bytes_per_step": int(res[True][1]), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": res[True][0] * 1e3, "host_buffers": "page-locked (pinned)",
+               "path": "mistra_kpp_integrate_rates: compact inputs of Update_RCONST_x + FIX + VAR to the device, "
+                       "expand -> Update_RCONST_x -> INTEGRATE_x there, VAR + diagnostics back",
+               "rconst_path": {"value": total_cells / res[False][0], "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                               "ms_per_step": res[False][0] * 1e3,
+                               "path": "mistra_kpp_integrate: RCONST evaluated by the host beforehand (outside the clock) and shipped"}}
         # the same call with PAGEABLE host arrays (what a Fortran caller has unless it registers its arrays with
         # mistra_kpp_host_register): copies are staged by the driver and do not overlap the kernels
         if world == 1 and not args.no_extras:
@@ -590,7 +616,7 @@ def run_b200(args):
                 torch.cuda.synchronize()
                 dtp.append(time.perf_counter() - t0)
             e2e["pageable"] = {"value": total_cells / min(dtp[1:]), "unit": UNIT, "ms_per_step": min(dtp[1:]) * 1e3,
-                               "note": "same call, plain numpy (pageable) arrays for rconst, fix, var and the diagnostics"}
+                               "note": "mistra_kpp_integrate (RCONST path) with plain numpy (pageable) arrays for rconst, fix, var and the diagnostics"}
             del pg, work
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------

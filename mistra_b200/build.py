@@ -74,7 +74,8 @@ def _deps(unit):
         deps += [os.path.join(CSRC, "_gen", "onchip_%s.cuh" % x), os.path.join(CSRC, "ros3_onchip.inc"),
                  os.path.join(CSRC, "kpp_onchip.h")]
     if unit == "kpp_api.cu":
-        deps.append(os.path.join(CSRC, "kpp_onchip.h"))
+        deps += [os.path.join(CSRC, "kpp_onchip.h"), os.path.join(ROOT, "include", "mistra_kpp_rates.h"),
+                 os.path.join(ROOT, "include", "mistra_rconst_cuda.h"), os.path.join(ROOT, "include", "mistra_rconst.h")]
     return deps
 
 

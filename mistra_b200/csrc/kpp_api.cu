@@ -4,6 +4,8 @@
 // CUDA device.
 #include "../../include/mistra_kpp.h"
 #include "kpp_onchip.h"
+#include "../../include/mistra_kpp_rates.h"
+#include "../../include/mistra_rconst_cuda.h"
 
 #include <atomic>
 #include <cmath>
@@ -49,6 +51,8 @@ struct DeviceState {
   // device staging for the host-buffer entry
   void *d_stage = nullptr;
   size_t d_stage_bytes = 0;
+  void *d_rates = nullptr;            // scratch of mistra_kpp_integrate_rates (expanded rate arrays, two slots)
+  size_t d_rates_bytes = 0;
   // copy streams / events of the chunk pipeline of the host-buffer entry
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_k2 = nullptr;
   cudaEvent_t ev_h[64] = {}, ev_k[64] = {}, ev_start = nullptr, ev_join = nullptr;
@@ -295,6 +299,29 @@ int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rcons
   g_launches.fetch_add(1);
   g_launches_variant[onchip ? 1 : 0].fetch_add(1);
   return 0;
+}
+
+
+// ---- compact rate inputs -> the NSPEC-indexed arrays Update_RCONST_x reads (include/mistra_kpp_rates.h) ------------
+__global__ void rates_expand_kernel(double *__restrict__ full, const double *__restrict__ val, const int *__restrict__ idx,
+                                    long long nrow, int n, int nspec)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // (row = cell * nk + k, j)
+  if (i >= nrow * n) return;
+  const long long row = i / n;
+  const int j = (int)(i - row * n);
+  full[row * nspec + idx[j]] = val[i];
+}
+
+__global__ void rates_conc_kernel(double *__restrict__ conc, const double *__restrict__ var, const double *__restrict__ fix,
+                                  long long ncell, int nvar, int nfix)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nspec = nvar + nfix;
+  if (i >= ncell * nspec) return;
+  const long long c = i / nspec;
+  const int s = (int)(i - c * nspec);
+  conc[i] = s < nvar ? var[c * nvar + s] : fix[c * nfix + (s - nvar)];
 }
 
 int ensure_streams(DeviceState *d)
@@ -547,6 +574,200 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
   return rc;
 }
 
+
+int mistra_kpp_integrate_rates(int mech, int64_t ncell, const mistra_rate_inputs_compact *rates, const double *fix,
+                               double *var, double t0, double t1, const mistra_kpp_opts *o, int32_t *ierr,
+                               int32_t *stats, double *hexit, double *texit, int64_t *h2d_bytes, void *stream)
+{
+  const KppMechInfo *mi = mech_info(mech);
+  if (!mi) return fail(MISTRA_KPP_EINVAL, "unknown mechanism id");
+  if (ncell < 0) return fail(MISTRA_KPP_EINVAL, "ncell < 0");
+  if (!rates) return fail(MISTRA_KPP_EINVAL, "null rates");
+  if (ncell > 0 && (!fix || !var || !rates->cb1 || !rates->scal || !rates->ph_rat))
+    return fail(MISTRA_KPP_EINVAL, "null fix / var / cb1 / scal / ph_rat");
+  {
+    KppBatch tmp;
+    int rc = decode_opts(o, t0, t1, &tmp);
+    if (rc) return rc;
+  }
+  const int nspec = mi->nvar + mi->nfix, nkc = (mech == MISTRA_KPP_TOT) ? 4 : 2;
+  struct L { const mistra_rate_list *l; int nk; } lists[6] = {{&rates->yhenry, 1}, {&rates->yxkmt, nkc}, {&rates->ykef, nkc},
+                                                              {&rates->ykeb, nkc}, {&rates->yxkmtd, 2}, {&rates->yxeq, 1}};
+  for (auto &q : lists) {
+    if (q.l->n < 0 || q.l->n > nspec) return fail(MISTRA_KPP_EINVAL, "rate list: bad species count");
+    if (q.l->n > 0 && (!q.l->idx || !q.l->val)) return fail(MISTRA_KPP_EINVAL, "rate list: null idx / val");
+    for (int j = 0; j < q.l->n; ++j)
+      if (q.l->idx[j] < 0 || q.l->idx[j] >= nspec) return fail(MISTRA_KPP_EINVAL, "rate list: species index out of range");
+  }
+  if (h2d_bytes) *h2d_bytes = 0;
+  DeviceState *d;
+  int rc;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    rc = get_device(&d);
+  }
+  if (rc) return rc;
+  std::lock_guard<std::mutex> dl(g_dev_mu[d->dev]);
+  cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+  if (ncell == 0) return 0;
+  const bool oc = want_onchip(mi, mech, ncell);
+  if ((rc = ensure_mech(*d, mech, mi, o ? (o->f32_literals ? 1 : 0) : 1, st, oc))) return rc;
+  if ((rc = ensure_streams(d))) return rc;
+
+  // chunks: as mistra_kpp_integrate, but at most 65536 cells each (the expanded rate arrays are per chunk)
+  const int64_t resident = oc ? (int64_t)d->mech[mech].oc_blocks * mi->oc->slots : (int64_t)d->mech[mech].blocks * KPP_BLOCK;
+  int64_t nchunk = ncell / (2 * resident);
+  if (nchunk < 1) nchunk = 1;
+  if (nchunk > 16) nchunk = 16;
+  if ((ncell + nchunk - 1) / nchunk > 65536) nchunk = (ncell + 65535) / 65536;
+  if (nchunk > 64) return fail(MISTRA_KPP_EINVAL, "batch too large for one call (more than 64 x 65536 cells)");
+  const int64_t per = (ncell + nchunk - 1) / nchunk;
+
+  // ---- device staging of the whole batch: fix | var | diagnostics | scalars | compact lists | index lists
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t n = (size_t)ncell;
+  const size_t b_fx = al(n * mi->nfix * 8), b_vr = al(n * mi->nvar * 8), b_hx = al(n * 8), b_ie = al(n * 4), b_st = al(n * 32);
+  const size_t b_cb = al(n * 4 * 8), b_sc = al(n * 13 * 8), b_ph = al(n * 47 * 8), b_cw = al(n * nkc * 8), b_cd = al(n * 2 * 8);
+  size_t b_val[6], b_idx[6], tot_lists = 0;
+  for (int q = 0; q < 6; ++q) {
+    b_val[q] = al(n * lists[q].nk * (size_t)lists[q].l->n * 8);
+    b_idx[q] = al((size_t)lists[q].l->n * 4 + 4);
+    tot_lists += b_val[q] + b_idx[q];
+  }
+  const size_t total = b_fx + b_vr + 2 * b_hx + b_ie + b_st + b_cb + b_sc + b_ph + b_cw + b_cd + tot_lists;
+  if (d->d_stage_bytes < total) {
+    CK(cudaDeviceSynchronize());
+    if (d->d_stage) cudaFree(d->d_stage);
+    d->d_stage = nullptr;
+    d->d_stage_bytes = 0;
+    CK(cudaMalloc(&d->d_stage, total));
+    d->d_stage_bytes = total;
+  }
+  char *p = (char *)d->d_stage;
+  double *d_fx = (double *)p; p += b_fx;
+  double *d_vr = (double *)p; p += b_vr;
+  double *d_hx = (double *)p; p += b_hx;
+  double *d_tx = (double *)p; p += b_hx;
+  int32_t *d_ie = (int32_t *)p; p += b_ie;
+  int32_t *d_st = (int32_t *)p; p += b_st;
+  double *d_cb = (double *)p; p += b_cb;
+  double *d_sc = (double *)p; p += b_sc;
+  double *d_ph = (double *)p; p += b_ph;
+  double *d_cw = (double *)p; p += b_cw;
+  double *d_cd = (double *)p; p += b_cd;
+  double *d_val[6];
+  int *d_idx[6];
+  for (int q = 0; q < 6; ++q) { d_val[q] = (double *)p; p += b_val[q]; d_idx[q] = (int *)p; p += b_idx[q]; }
+
+  // ---- per-slot scratch: RCONST of a chunk and the NSPEC-indexed arrays (zero outside the lists, set once per call)
+  const size_t c_rc = al((size_t)per * mi->nreact * 8);
+  const int nk_full[7] = {1, nkc, nkc, nkc, 2, 1, 1};                 // yhenry yxkmt ykef ykeb yxkmtd yxeq | conc
+  size_t c_full[7], c_slot = c_rc;
+  for (int q = 0; q < 7; ++q) { c_full[q] = al((size_t)per * nk_full[q] * nspec * 8); c_slot += c_full[q]; }
+  if (d->d_rates_bytes < 2 * c_slot) {
+    CK(cudaDeviceSynchronize());
+    if (d->d_rates) cudaFree(d->d_rates);
+    d->d_rates = nullptr;
+    d->d_rates_bytes = 0;
+    CK(cudaMalloc(&d->d_rates, 2 * c_slot));
+    d->d_rates_bytes = 2 * c_slot;
+  }
+  double *s_rc[2], *s_full[2][7];
+  for (int sl = 0; sl < 2; ++sl) {
+    char *q = (char *)d->d_rates + sl * c_slot;
+    s_rc[sl] = (double *)q; q += c_rc;
+    for (int k = 0; k < 7; ++k) { s_full[sl][k] = (double *)q; q += c_full[k]; }
+  }
+  int64_t moved = 0;
+  auto pipeline = [&]() -> int {
+    CK(cudaEventRecord(d->ev_start, st));
+    CK(cudaStreamWaitEvent(d->s_h2d, d->ev_start, 0));
+    CK(cudaStreamWaitEvent(d->s_d2h, d->ev_start, 0));
+    CK(cudaStreamWaitEvent(d->s_k2, d->ev_start, 0));
+    for (int sl = 0; sl < 2; ++sl)          // entries outside the index lists stay zero for the whole call
+      CK(cudaMemsetAsync(s_full[sl][0], 0, c_slot - c_rc, sl ? d->s_k2 : st));
+    for (int q = 0; q < 6; ++q)
+      if (lists[q].l->n > 0) {
+        CK(cudaMemcpyAsync(d_idx[q], lists[q].l->idx, (size_t)lists[q].l->n * 4, cudaMemcpyHostToDevice, d->s_h2d));
+        moved += (int64_t)lists[q].l->n * 4;
+      }
+    for (int64_t c = 0, off = 0; off < ncell; ++c, off += per) {
+      const int slot = (int)(c & 1);
+      cudaStream_t ks = slot ? d->s_k2 : st;
+      const size_t m = (size_t)((ncell - off) < per ? (ncell - off) : per), o0 = (size_t)off;
+      auto up = [&](double *dst, const double *src, size_t w) -> cudaError_t {
+        moved += (int64_t)(m * w * 8);
+        return cudaMemcpyAsync(dst + o0 * w, src + o0 * w, m * w * 8, cudaMemcpyHostToDevice, d->s_h2d);
+      };
+      CK(up(d_fx, fix, mi->nfix));
+      CK(up(d_vr, var, mi->nvar));
+      CK(up(d_cb, rates->cb1, 4));
+      CK(up(d_sc, rates->scal, 13));
+      CK(up(d_ph, rates->ph_rat, 47));
+      if (rates->ycw) CK(up(d_cw, rates->ycw, nkc));
+      if (rates->ycwd) CK(up(d_cd, rates->ycwd, 2));
+      for (int q = 0; q < 6; ++q)
+        if (lists[q].l->n > 0) CK(up(d_val[q], lists[q].l->val, (size_t)lists[q].nk * lists[q].l->n));
+      CK(cudaEventRecord(d->ev_h[c], d->s_h2d));
+      CK(cudaStreamWaitEvent(ks, d->ev_h[c], 0));
+      // expand -> Update_RCONST_x -> INTEGRATE_x on the chunk's stream
+      for (int q = 0; q < 6; ++q) {
+        const int nl = lists[q].l->n;
+        if (nl == 0) continue;
+        const long long nrow = (long long)m * lists[q].nk, tot = nrow * nl;
+        rates_expand_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ks>>>(s_full[slot][q], d_val[q] + o0 * lists[q].nk * nl,
+                                                                             d_idx[q], nrow, nl, nspec);
+      }
+      {
+        const long long tot = (long long)m * nspec;
+        rates_conc_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ks>>>(s_full[slot][6], d_vr + o0 * mi->nvar, d_fx + o0 * mi->nfix,
+                                                                         (long long)m, mi->nvar, mi->nfix);
+      }
+      CK(cudaGetLastError());
+      mistra_rate_inputs in;
+      memset(&in, 0, sizeof in);
+      in.ncell = (int64_t)m;
+      in.cb1 = d_cb + o0 * 4; in.scal = d_sc + o0 * 13; in.ph_rat = d_ph + o0 * 47; in.conc = s_full[slot][6];
+      in.yhenry = s_full[slot][0]; in.yxkmt = s_full[slot][1]; in.ykef = s_full[slot][2]; in.ykeb = s_full[slot][3];
+      in.yxkmtd = s_full[slot][4]; in.yxeq = s_full[slot][5];
+      in.ycw = rates->ycw ? d_cw + o0 * nkc : nullptr;
+      in.ycwd = rates->ycwd ? d_cd + o0 * 2 : nullptr;
+      in.f32_literals = rates->f32_literals;
+      if (int r2 = mistra_rconst_update_device(mech, &in, s_rc[slot], ks)) return r2;
+      int r3 = launch_device(*d, mech, (int64_t)m, s_rc[slot], d_fx + o0 * mi->nfix, d_vr + o0 * mi->nvar, t0, t1, o,
+                             ierr ? d_ie + o0 : nullptr, stats ? d_st + o0 * 8 : nullptr, hexit ? d_hx + o0 : nullptr,
+                             texit ? d_tx + o0 : nullptr, ks, slot, oc);
+      if (r3) return r3;
+      CK(cudaEventRecord(d->ev_k[c], ks));
+    }
+    for (int64_t c = 0, off = 0; off < ncell; ++c, off += per) {
+      const size_t m = (size_t)((ncell - off) < per ? (ncell - off) : per), o0 = (size_t)off;
+      CK(cudaStreamWaitEvent(d->s_d2h, d->ev_k[c], 0));
+      CK(cudaMemcpyAsync(var + o0 * mi->nvar, d_vr + o0 * mi->nvar, m * mi->nvar * 8, cudaMemcpyDeviceToHost, d->s_d2h));
+      if (ierr) CK(cudaMemcpyAsync(ierr + o0, d_ie + o0, m * 4, cudaMemcpyDeviceToHost, d->s_d2h));
+      if (stats) CK(cudaMemcpyAsync(stats + o0 * 8, d_st + o0 * 8, m * 32, cudaMemcpyDeviceToHost, d->s_d2h));
+      if (hexit) CK(cudaMemcpyAsync(hexit + o0, d_hx + o0, m * 8, cudaMemcpyDeviceToHost, d->s_d2h));
+      if (texit) CK(cudaMemcpyAsync(texit + o0, d_tx + o0, m * 8, cudaMemcpyDeviceToHost, d->s_d2h));
+    }
+    CK(cudaEventRecord(d->ev_join, d->s_k2));
+    CK(cudaStreamWaitEvent(st, d->ev_join, 0));
+    CK(cudaStreamSynchronize(d->s_d2h));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+  };
+  rc = pipeline();
+  if (rc) {
+    const std::string msg = g_err;
+    cudaStreamSynchronize(d->s_h2d);
+    cudaStreamSynchronize(d->s_k2);
+    cudaStreamSynchronize(d->s_d2h);
+    cudaStreamSynchronize(st);
+    g_err = msg;
+  }
+  if (h2d_bytes) *h2d_bytes = moved;
+  return rc;
+}
+
 int64_t mistra_kpp_launch_count(void) { return g_launches.load(); }
 
 // ---- page-locked host memory: what lets the chunk pipeline overlap its copies with the kernels ----------------
@@ -693,6 +914,7 @@ int mistra_kpp_finalize(void)
     if (d.counter) cudaFree(d.counter);
     for (auto &e : d.ev_slot) if (e) cudaEventDestroy(e);
     if (d.d_stage) cudaFree(d.d_stage);
+    if (d.d_rates) cudaFree(d.d_rates);
     if (d.s_h2d) {
       cudaStreamDestroy(d.s_h2d);
       cudaStreamDestroy(d.s_d2h);

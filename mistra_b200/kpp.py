@@ -226,6 +226,142 @@ def host_unregister(a, strict=False):
     _check(L, L.mistra_kpp_host_unregister(C.c_void_p(a.ctypes.data)))
 
 
+class RateList(C.Structure):
+    _fields_ = [("n", C.c_int32), ("reserved", C.c_int32), ("idx", C.POINTER(C.c_int32)), ("val", C.POINTER(C.c_double))]
+
+
+class RateInputsCompact(C.Structure):
+    _fields_ = [("cb1", C.POINTER(C.c_double)), ("scal", C.POINTER(C.c_double)), ("ph_rat", C.POINTER(C.c_double)),
+                ("ycw", C.POINTER(C.c_double)), ("ycwd", C.POINTER(C.c_double)),
+                ("yhenry", RateList), ("yxkmt", RateList), ("ykef", RateList), ("ykeb", RateList),
+                ("yxkmtd", RateList), ("yxeq", RateList), ("f32_literals", C.c_int32), ("reserved", C.c_int32)]
+
+
+class CompactRates:
+    """What Update_RCONST_x reads, in the compact form of include/mistra_kpp_rates.h: the per-layer scalars as they
+    are, the KPP-species-indexed exchange arrays only for the species that are non-zero somewhere in the batch
+    (one index list per array).  Built from the full arrays of include/mistra_rconst.h; keeps its buffers alive."""
+
+    LISTS = ("yhenry", "yxkmt", "ykef", "ykeb", "yxkmtd", "yxeq")
+
+    def __init__(self, mech, cb1, scal, ph_rat, ycw=None, ycwd=None, f32_literals=1, alloc=None, idx=None, **full):
+        nvar, nfix, _, _ = query(mech)
+        nspec = nvar + nfix
+        self.mech = mech
+        self.f32 = int(f32_literals)
+        self.ncell = int(np.asarray(cb1).shape[0])
+        alloc = alloc or (lambda shape, dtype: np.empty(shape, dtype=dtype))
+
+        def own(a, w):
+            if a is None:
+                return None
+            out = alloc((self.ncell, w), np.float64)
+            out[...] = np.asarray(a, dtype=np.float64).reshape(self.ncell, w)
+            return out
+        self.cb1, self.scal, self.ph_rat = own(cb1, 4), own(scal, 13), own(ph_rat, 47)
+        nkc = 4 if mech == 2 else 2
+        self.ycw, self.ycwd = own(ycw, nkc), own(ycwd, 2)
+        self.idx, self.val = {}, {}
+        for name in self.LISTS:
+            a = full.get(name)
+            if a is None:
+                self.idx[name], self.val[name] = np.zeros(0, dtype=np.int32), None
+                continue
+            a = np.asarray(a, dtype=np.float64).reshape(self.ncell, -1, nspec)
+            used = np.nonzero((a != 0.0).any(axis=(0, 1)))[0].astype(np.int32)
+            if idx is not None:                      # a given list (e.g. of another slice of the same ensemble)
+                if not set(used.tolist()) <= set(idx[name].tolist()):
+                    raise KppError("CompactRates: %s has non-zero species outside the given index list" % name)
+                used = np.ascontiguousarray(idx[name], dtype=np.int32)
+            self.idx[name] = used
+            v = alloc((self.ncell, a.shape[1], len(used)), np.float64)
+            v[...] = a[:, :, used]
+            self.val[name] = v
+        self._bind()
+
+    @classmethod
+    def concat(cls, parts, alloc=None):
+        """The batch made of the cells of `parts` (same mechanism, same index lists), buffers from `alloc`."""
+        alloc = alloc or (lambda shape, dtype: np.empty(shape, dtype=dtype))
+        self = cls.__new__(cls)
+        p0 = parts[0]
+        self.mech, self.f32 = p0.mech, p0.f32
+        self.ncell = sum(p.ncell for p in parts)
+
+        def cat(arrs):
+            if arrs[0] is None:
+                return None
+            out = alloc((self.ncell,) + arrs[0].shape[1:], np.float64)
+            o = 0
+            for a in arrs:
+                out[o:o + a.shape[0]] = a
+                o += a.shape[0]
+            return out
+        for k in ("cb1", "scal", "ph_rat", "ycw", "ycwd"):
+            setattr(self, k, cat([getattr(p, k) for p in parts]))
+        self.idx = {n: p0.idx[n].copy() for n in cls.LISTS}
+        for p in parts[1:]:
+            for n in cls.LISTS:
+                if not np.array_equal(p.idx[n], p0.idx[n]):
+                    raise KppError("CompactRates.concat: index lists differ")
+        self.val = {n: cat([p.val[n] for p in parts]) for n in cls.LISTS}
+        self._bind()
+        return self
+
+    def _bind(self):
+        dp = C.POINTER(C.c_double)
+        s = RateInputsCompact()
+        for k in ("cb1", "scal", "ph_rat", "ycw", "ycwd"):
+            a = getattr(self, k)
+            setattr(s, k, a.ctypes.data_as(dp) if a is not None else None)
+        for name in self.LISTS:
+            rl = RateList()
+            rl.n = len(self.idx[name])
+            if rl.n:
+                rl.idx = self.idx[name].ctypes.data_as(C.POINTER(C.c_int32))
+                rl.val = self.val[name].ctypes.data_as(dp)
+            setattr(s, name, rl)
+        s.f32_literals = self.f32
+        self.struct = s
+
+    @property
+    def nbytes(self):
+        n = sum(a.nbytes for a in (self.cb1, self.scal, self.ph_rat, self.ycw, self.ycwd) if a is not None)
+        return n + sum(v.nbytes for v in self.val.values() if v is not None) + sum(i.nbytes for i in self.idx.values())
+
+
+def integrate_rates(mech, rates, fix, var, t0=0.0, t1=10.0, opts=None, out=None, diag=None):
+    """mistra_kpp_integrate_rates: like integrate(), with the rate constants formed on the device from `rates`
+    (a CompactRates).  Returns (var_out, ierr, stats, hexit, texit, h2d_bytes)."""
+    L = library()
+    nvar, nfix, nreact, _ = query(mech)
+    var_in = np.ascontiguousarray(var, dtype=np.float64).reshape(-1, nvar)
+    ncell = var_in.shape[0]
+    if ncell != rates.ncell:
+        raise KppError("integrate_rates: rates are for %d cells, var has %d" % (rates.ncell, ncell))
+    var_out = out if out is not None else np.empty_like(var_in)
+    if var_out.ctypes.data != var_in.ctypes.data:
+        np.copyto(var_out, var_in)
+    fix = np.ascontiguousarray(fix, dtype=np.float64).reshape(ncell, nfix)
+    if diag is not None:
+        ierr, stats, hexit, texit = diag
+    else:
+        ierr = np.zeros(ncell, dtype=np.int32)
+        stats = np.zeros((ncell, 8), dtype=np.int32)
+        hexit = np.zeros(ncell, dtype=np.float64)
+        texit = np.zeros(ncell, dtype=np.float64)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    o = opts if opts is not None else default_opts()
+    moved = C.c_int64(0)
+    L.mistra_kpp_integrate_rates.argtypes = [C.c_int, C.c_int64, C.POINTER(RateInputsCompact), dp, dp, C.c_double, C.c_double,
+                                             C.POINTER(KppOpts), ip, ip, dp, dp, C.POINTER(C.c_int64), C.c_void_p]
+    rc = L.mistra_kpp_integrate_rates(mech, ncell, C.byref(rates.struct), fix.ctypes.data_as(dp), var_out.ctypes.data_as(dp),
+                                      t0, t1, C.byref(o), ierr.ctypes.data_as(ip), stats.ctypes.data_as(ip),
+                                      hexit.ctypes.data_as(dp), texit.ctypes.data_as(dp), C.byref(moved), None)
+    _check(L, rc)
+    return var_out, ierr, stats, hexit, texit, int(moved.value)
+
+
 def set_kernel(mech, variant, strict=False):
     """Kernel variant of a mechanism: -1 = by batch size (default), 0 = one cell per thread, 1 = on-chip (gas, aer)."""
     L = library(strict)

@@ -173,6 +173,12 @@ class GasEnsemble:
     def conc(self, var=None):
         return np.concatenate([self.var if var is None else var, self.fix], axis=1)
 
+    def compact_rates(self, alloc=None, idx=None):
+        """The inputs of Update_RCONST_g in the compact form of include/mistra_kpp_rates.h."""
+        from . import kpp
+        return kpp.CompactRates(0, self.cb1, self.scal, self.ph_rat, ycwd=self.ycwd, f32_literals=self.f32, alloc=alloc,
+                                idx=idx, yhenry=self.yhenry, yxkmtd=self.yxkmtd, yxeq=self.yxeq)
+
     def rconst(self, var=None, sl=slice(None)):
         """Update_RCONST_g for the cells in `sl` at concentrations `var`."""
         c = self.conc(var)[sl]
@@ -359,6 +365,13 @@ class _AqueousEnsemble:
 
     def conc(self, var=None):
         return np.concatenate([self.var if var is None else var, self.fix], axis=1)
+
+    def compact_rates(self, alloc=None, idx=None):
+        """The inputs of Update_RCONST_a / _t in the compact form of include/mistra_kpp_rates.h."""
+        from . import kpp
+        return kpp.CompactRates(self.mech, self.cb1, self.scal, self.ph_rat, ycw=self.ycw, ycwd=self.ycwd,
+                                f32_literals=self.f32, alloc=alloc, idx=idx, yhenry=self.yhenry, yxkmt=self.yxkmt, ykef=self.ykef,
+                                ykeb=self.ykeb, yxkmtd=self.yxkmtd, yxeq=self.yxeq)
 
     def rconst(self, var=None, sl=slice(None)):
         """Update_RCONST_a / _t for the cells in `sl` at concentrations `var`."""
