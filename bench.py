@@ -348,7 +348,7 @@ def run_extras(args, dev, batches, dbatches):
         oc = roof("aer", stats, ms, n)
         oc["kernel"] = "ros3_onchip_a (one persistent block per SM, 5 cell slots, LU in shared memory / registers)"
         oc["cell_per_thread_kernel_same_cells"] = {"kernel_ms": msd, "cells_per_s": n / (msd * 1e-3)}
-        oc["dram_bytes_per_cell"] = {"value": 10.2e3, "compulsory": 11984,
+        oc["dram_bytes_per_cell"] = {"value": 14.7e3, "compulsory": 11984,
                                      "source": "ncu --set full capture profiles/r02_onchip_aer_ncu_full.txt (dram read+write / cells)"}
         res["onchip_aer"] = oc
 
