@@ -111,8 +111,10 @@ RL_HD double fbck2(const rate_ctx *cx, double a1, double a2, double b1, double b
   double a0 = a1 * cx->aircc * pow(cx->te / 300., a2);
   double b0 = b1 * pow(cx->te / 300., b2);
   double x1 = rl_troe(a0, b0, fc);
-  double q = cx->f32 ? (double)(8.314f / 101325.f) : 8.314 / 101325.;
-  if (ck != 0.0) return x1 / (ak * exp(bk / cx->te) * q * cx->te / ck);
+  // kpp.f90:7437  x1/(ak*exp(bk/te)*8.314/101325.*te/ck): evaluated left to right, so each default-REAL literal is
+  // promoted to double when it meets the running product - they are never divided by each other in single precision
+  // (found by the independent evaluator tests/golden/make_rconst_reference.py: 1.7e-8 relative)
+  if (ck != 0.0) return x1 / (ak * exp(bk / cx->te) * RL(8.314) / RL(101325.) * cx->te / ck);
   return 0.0;
 }
 
