@@ -33,14 +33,19 @@ def _lib():
     return L
 
 
-def drive_map(mech_name, gas_names, rad_names, j2=121, j6=55):
+def drive_map(mech_name, gas_names, rad_names, j2=121, j6=55, allow_unmatched=False):
     """The copy list of <mech>_drive: s1 / s3 entries matched by species name as match_mk_indexes does
-    (utils.f90:84-140; names absent from the mechanism are left out), sl1 / sion1 entries from
+    (utils.f90:84-140).  A user species name that the mechanism does not know aborts the reference
+    (utils.f90:1052-1056); so it does here (ValueError) unless allow_unmatched=True, which leaves such names out - a
+    misspelt name would otherwise be neither gathered nor scattered, silently.  sl1 / sion1 entries from
     aer_mk.dat / tot.f (mistra_b200/mech/drive_maps.json; none for the gas mechanism, whose six sl1
     reads - gas.f:151-156 - the caller appends).  Returns dict(kpp, arr, off) of int32 arrays and the FIX
     positions indf_*."""
     m = mechmod.load(mech_name)
     pos = {s: i + 1 for i, s in enumerate(m.spc_names)}
+    missing = [s for s in list(gas_names) + list(rad_names) if s not in pos]
+    if missing and not allow_unmatched:
+        raise ValueError("drive_map: species not in mechanism %s: %s" % (mech_name, ", ".join(missing)))
     ent = [(pos[s], 0, j) for j, s in enumerate(gas_names) if s in pos]
     ent += [(pos[s], 1, j) for j, s in enumerate(rad_names) if s in pos]
     if mech_name in ("aer", "tot"):

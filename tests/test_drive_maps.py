@@ -6,6 +6,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 from mistra_b200 import drive
 from mistra_b200.mechgen import mech as mechmod
@@ -45,10 +46,18 @@ def test_tables_resolve_and_invert():
         assert max(e[2] for e in g if e[1] == "sl1") <= J2 and max(e[2] for e in g if e[1] == "sion1") <= J6
 
 
+def test_unknown_species_names_abort_like_the_reference():
+    """match_mk_indexes stops the model on a user species the mechanism does not know (utils.f90:1052-1056)."""
+    gn, rn = name_lists("aer")
+    with pytest.raises(ValueError, match="XYZ_unknown"):
+        drive.drive_map("aer", gn, rn)
+    assert len(drive.drive_map("aer", gn, rn, allow_unmatched=True)["kpp"]) == len(gn) + len(rn) - 2 + 79 * 2
+
+
 def test_oracle_gather_scatter():
     for mech in ("aer", "tot", "gas"):
         gn, rn = name_lists(mech)
-        mp = drive.drive_map(mech, gn, rn)
+        mp = drive.drive_map(mech, gn, rn, allow_unmatched=True)
         m = mechmod.load(mech)
         assert mp["indf_o2"] and mp["indf_h2o"] and mp["indf_n2"]
         assert [bool(x) for x in mp["indf_h2ol"]] == {"aer": [1, 1, 0, 0], "tot": [1, 1, 1, 1], "gas": [0, 0, 0, 0]}[mech]

@@ -22,7 +22,7 @@ def test_gather_scatter_vs_oracle(cuda_device, kpp, mech, nl, nc, f32):
     import torch
     t = dev(cuda_device)
     gn, rn = name_lists(mech, seed=nl)
-    mp = drive.drive_map(mech, gn, rn)
+    mp = drive.drive_map(mech, gn, rn, allow_unmatched=True)
     md = drive.to_device(mp, cuda_device)
     m = mechmod.load(mech)
     st = state(nl, 3)
@@ -64,7 +64,7 @@ def test_chemistry_step_stays_on_the_device(cuda_device, kpp):
     m = mechmod.load("aer")
     nc = ens.ncell
     gn, rn = name_lists("aer", seed=1)
-    mp = drive.drive_map("aer", gn, rn)
+    mp = drive.drive_map("aer", gn, rn, allow_unmatched=True)
     md = drive.to_device(mp, cuda_device)
     nl = nc + 30
     layer = np.random.default_rng(2).permutation(nl)[:nc].astype(np.int64)
