@@ -55,9 +55,9 @@ def _deps(unit):
     if unit.startswith("konc_"):
         deps.append(os.path.join(ROOT, "include", "mistra_konc.h"))
     if unit.startswith("cwrc_"):
-        deps.append(os.path.join(ROOT, "include", "mistra_cwrc.h"))
+        deps += [os.path.join(ROOT, "include", "mistra_cwrc.h"), os.path.join(CSRC, "tma_bulk.h")]
     if unit.startswith("fastkmt_"):
-        deps.append(os.path.join(ROOT, "include", "mistra_fastkmt.h"))
+        deps += [os.path.join(ROOT, "include", "mistra_fastkmt.h"), os.path.join(CSRC, "tma_bulk.h")]
     if unit.startswith("difc_"):
         deps.append(os.path.join(ROOT, "include", "mistra_difc.h"))
     if unit.startswith("drive_"):

@@ -9,6 +9,7 @@
 // classes ia <= ka / large ones); one fixed butterfly per sum adds the lanes, twelve threads add the
 // warps in order and four apply the switches (2335-2410).  HBM-bound: nka*nkt*8 = 39.2 kB read per
 // layer, 128 B written.  No FMA contraction (build.py).
+#include "tma_bulk.h"
 #include "../../include/mistra_cwrc.h"
 #include "../../include/mistra_kpp.h"
 
@@ -43,21 +44,31 @@ __global__ void __launch_bounds__(CWRC_THREADS) cwrc_kernel(long long ncell, mis
   const double xpi = 4.0 / 3.0 * 3.1415926535897932;   // kpp.f90:2204, constants.f90 pi
   extern __shared__ __align__(16) double s_ff[];       // [nka][nkt] the layer's spectrum
   const int ntile = nka * nkt;
+  __shared__ unsigned long long s_bar;       // completion barrier of the tile's bulk copy
+  if (threadIdx.x == 0) tma::mbar_init(&s_bar, 1);
+  unsigned phase = 0;
   for (long long c = blockIdx.x; c < ncell; c += gridDim.x) {
     __syncthreads();
-    // the whole tile in flight at once (16-byte asynchronous copies, no register staging)
     const double *gf = a.ff + (size_t)c * ntile;
-    if ((ntile & 1) == 0) {
-      for (int q = threadIdx.x; q < (ntile >> 1); q += blockDim.x)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(s_ff + 2 * q)),
-                     "l"(gf + 2 * q) : "memory");
+    if (tma::bulk_ok(gf, (size_t)ntile * 8)) {
+      // the layer's 70 x 70 spectrum is one contiguous 39.2 kB block: ONE bulk (TMA) copy, completion on the mbarrier
+      if (threadIdx.x == 0) tma::bulk_load(s_ff, gf, (unsigned)(ntile * 8), &s_bar);
+      tma::mbar_wait(&s_bar, phase);
+      phase ^= 1u;
     } else {
-      for (int q = threadIdx.x; q < ntile; q += blockDim.x)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(s_ff + q)),
-                     "l"(gf + q) : "memory");
+      // unaligned caller buffer: 16- / 8-byte asynchronous copies (no register staging)
+      if ((ntile & 1) == 0 && ((reinterpret_cast<unsigned long long>(gf) & 15ull) == 0ull)) {
+        for (int q = threadIdx.x; q < (ntile >> 1); q += blockDim.x)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(s_ff + 2 * q)),
+                       "l"(gf + 2 * q) : "memory");
+      } else {
+        for (int q = threadIdx.x; q < ntile; q += blockDim.x)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(s_ff + q)),
+                       "l"(gf + q) : "memory");
+      }
+      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+      __syncthreads();
     }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-    __syncthreads();
     const double *f = s_ff;
     // one warp per dry class at a time: lanes stride over the water bins (coalesced loads of ff and
     // rq); each lane keeps, over all classes of its warp, the sums of the four chemistry bins

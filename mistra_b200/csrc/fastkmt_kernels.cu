@@ -16,6 +16,7 @@
 // warps in warp order.  Real spectra populate a few per cent of the grid, then the kernel streams
 // ff (39.2 kB per layer); with every point populated it is FP64-bound: (nx + 1) divisions per point.
 // No FMA contraction (build.py).
+#include "tma_bulk.h"
 #include "../../include/mistra_fastkmt.h"
 #include "../../include/mistra_kpp.h"
 
@@ -102,10 +103,16 @@ __device__ __forceinline__ FkSmem fk_carve(double *smem, int ntile)
   return s;
 }
 
-__device__ __forceinline__ void fk_fetch(double *dst, double *sc, const mistra_fastkmt_args &a, long long c, int ntile)
+// returns true if the tile travels by a bulk (TMA) copy whose completion is signalled on `bar`
+__device__ __forceinline__ bool fk_fetch(double *dst, double *sc, const mistra_fastkmt_args &a, long long c, int ntile,
+                                         unsigned long long *bar)
 {
   const double *gf = a.ff + (size_t)c * ntile;
-  if ((ntile & 1) == 0) {
+  const bool bulk = tma::bulk_ok(gf, (size_t)ntile * 8);
+  if (bulk) {
+    // the layer's spectrum is one contiguous 39.2 kB block: ONE bulk copy instead of 2450 16-byte copies
+    if (threadIdx.x == 0) tma::bulk_load(dst, gf, (unsigned)(ntile * 8), bar);
+  } else if ((ntile & 1) == 0 && ((reinterpret_cast<unsigned long long>(gf) & 15ull) == 0ull)) {
     for (int q = threadIdx.x; q < (ntile >> 1); q += FK_THREADS)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst + 2 * q)),
                    "l"(gf + 2 * q) : "memory");
@@ -126,6 +133,7 @@ __device__ __forceinline__ void fk_fetch(double *dst, double *sc, const mistra_f
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(sc + tq)), "l"(src)
                  : "memory");
   asm volatile("cp.async.commit_group;\n" ::: "memory");
+  return bulk;
 }
 
 __global__ void __launch_bounds__(FK_THREADS, 1) fastkmt_kernel(long long ncell, mistra_fastkmt_args a)
@@ -137,7 +145,12 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fastkmt_kernel(long long ncell,
   const double z4pi3 = 4.0 * 3.1415926535897932 / 3.0;   // kpp.f90:2758
   const int nx = a.nx, nspec = a.nspec, nkc = a.nkc;
 
-  if ((long long)blockIdx.x < ncell) fk_fetch(s.f0, s.sc, a, blockIdx.x, ntile);
+  __shared__ unsigned long long s_bar[2];    // completion barriers of the two tile buffers' bulk copies
+  if (threadIdx.x == 0) { tma::mbar_init(&s_bar[0], 1); tma::mbar_init(&s_bar[1], 1); }
+  __syncthreads();
+  unsigned phase = 0;                        // bit b: parity of buffer b's next completion
+  bool bulk_cur = false, bulk_nxt = false;
+  if ((long long)blockIdx.x < ncell) bulk_cur = fk_fetch(s.f0, s.sc, a, blockIdx.x, ntile, &s_bar[0]);
   for (int q = threadIdx.x; q < ntile; q += FK_THREADS) {
     const int ia = q / nkt, jt = q - ia * nkt;
     s.r[q] = a.rq[q] * 1.e-6;
@@ -152,7 +165,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fastkmt_kernel(long long ncell,
   for (long long c = blockIdx.x; c < ncell; c += gridDim.x, buf ^= 1) {
     __syncthreads();                         // the other buffer, the lists and the partial sums are free again
     const long long cn = c + gridDim.x;
-    if (cn < ncell) fk_fetch(s.f0 + (buf ^ 1) * s.npad, s.sc + (buf ^ 1) * 16, a, cn, ntile);
+    if (cn < ncell) bulk_nxt = fk_fetch(s.f0 + (buf ^ 1) * s.npad, s.sc + (buf ^ 1) * 16, a, cn, ntile, &s_bar[buf ^ 1]);
     // the species' accommodation coefficient and mean speed while the tile is in flight
     // (loads issued here, consumed in step 3).  Idle lanes: 1 / (q + 1), never stored - a zero numerator
     // would send the whole warp down the slow path of the division.
@@ -161,6 +174,11 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fastkmt_kernel(long long ncell,
     if (sp1 >= 0) { al1 = a.alpha[c * nspec + sp1]; vm1 = a.vmean[c * nspec + sp1]; }
     if (cn < ncell) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     else            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    if (bulk_cur) {
+      tma::mbar_wait(&s_bar[buf], (phase >> buf) & 1u);
+      phase ^= 1u << buf;
+    }
+    bulk_cur = bulk_nxt;
     __syncthreads();
     const double *sf = s.f0 + buf * s.npad, *sc = s.sc + buf * 16;
     const double freep = sc[8], tk = sc[9], pk = sc[10];

@@ -428,24 +428,32 @@ int mistra_kpp_integrate_device(int mech, int64_t ncell, const double *d_rconst,
   if (rc) return rc;
   std::lock_guard<std::mutex> dl(g_dev_mu[d->dev]);
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream, as in the CUDA runtime
-  // A long batch runs as two co-resident kernels over its two halves (second stream, second workspace): when the
-  // lanes of one half run out of cells the other half still has work, so the device does not idle through the
-  // tail of a single launch (aer, 588 000 cells: +3 %, measured; this is also why the chunked host-buffer entry
-  // used to beat the single device launch).  MISTRA_KPP_SPLIT=0 switches it off.
+  // A long batch runs as a chain of chunks that alternate between two streams / workspaces (as the host-buffer entry
+  // does): while the lanes of one chunk run out of cells the next chunk already has its blocks on the device, so the
+  // SMs do not idle through the tail of one big launch while its slowest cells finish (aer, 588 000 cells: two halves
+  // +3 %, sixteen chunks more; measured).  MISTRA_KPP_SPLIT=0 switches it off.
   static const bool split = !(getenv("MISTRA_KPP_SPLIT") && atoi(getenv("MISTRA_KPP_SPLIT")) == 0);
   const bool oc = want_onchip(mech_info(mech), mech, ncell);
   if (split && !oc && ncell >= 8LL * d->num_sm * 2 * KPP_BLOCK) {
     const KppMechInfo *mi = mech_info(mech);
     if ((rc = ensure_streams(d))) return rc;
-    const int64_t h = ncell / 2;
+    if ((rc = ensure_mech(*d, mech, mi, o ? (o->f32_literals ? 1 : 0) : 1, st, false))) return rc;
+    const int64_t resident = (int64_t)d->mech[mech].blocks * KPP_BLOCK;
+    int64_t nchunk = ncell / (2 * resident);
+    if (nchunk < 2) nchunk = 2;
+    if (nchunk > 16) nchunk = 16;
+    const int64_t per = (ncell + nchunk - 1) / nchunk;
     CK(cudaEventRecord(d->ev_start, st));
     CK(cudaStreamWaitEvent(d->s_k2, d->ev_start, 0));
-    if ((rc = launch_device(*d, mech, h, d_rconst, d_fix, d_var, t0, t1, o, d_ierr, d_stats, d_hexit, d_texit, st, 0, false)))
-      return rc;
-    if ((rc = launch_device(*d, mech, ncell - h, d_rconst + h * mi->nreact, d_fix + h * mi->nfix, d_var + h * mi->nvar,
-                            t0, t1, o, d_ierr ? d_ierr + h : nullptr, d_stats ? d_stats + 8 * h : nullptr,
-                            d_hexit ? d_hexit + h : nullptr, d_texit ? d_texit + h : nullptr, d->s_k2, 1, false)))
-      return rc;
+    for (int64_t c = 0, off = 0; off < ncell; ++c, off += per) {
+      const int slot = (int)(c & 1);
+      const int64_t m = (ncell - off) < per ? (ncell - off) : per;
+      if ((rc = launch_device(*d, mech, m, d_rconst + off * mi->nreact, d_fix + off * mi->nfix, d_var + off * mi->nvar,
+                              t0, t1, o, d_ierr ? d_ierr + off : nullptr, d_stats ? d_stats + 8 * off : nullptr,
+                              d_hexit ? d_hexit + off : nullptr, d_texit ? d_texit + off : nullptr,
+                              slot ? d->s_k2 : st, slot, false)))
+        return rc;
+    }
     CK(cudaEventRecord(d->ev_join, d->s_k2));
     CK(cudaStreamWaitEvent(st, d->ev_join, 0));
     return 0;
