@@ -85,10 +85,12 @@ const char *mistra_kpp_spc_name(int mech, int i);
  *   stats  [ncell][8]       Nfun,Njac,Nstp,Nacc,Nrej,Ndec,Nsol,Nsng (gas.f:913-915) or NULL
  *   hexit  [ncell]          last step size = STEPMIN on return of INTEGRATE_x (gas.f:770) or NULL
  *   texit  [ncell]          time reached = TIN on return of INTEGRATE_x (gas.f:769) or NULL
- * Row-major C arrays = Fortran arrays (NREACT,ncell) etc.  HOST buffers; the call
- * stages them through pinned memory to the current CUDA device, runs, copies the
- * results back and returns when they are in place.  `stream` is a cudaStream_t
- * (NULL = the library's own stream). */
+ * Row-major C arrays = Fortran arrays (NREACT,ncell) etc.  HOST buffers: the call copies them chunk by chunk
+ * (cudaMemcpyAsync straight from / to the caller's arrays) to the current CUDA device, runs the chunks on two
+ * alternating streams, copies the results back and returns when they are in place.  Pageable arrays work as they
+ * are; only page-locked ones (mistra_kpp_host_alloc / mistra_kpp_host_register below) let the copies overlap the
+ * kernels.  On a failure in the middle of the pipeline every stream is drained before the error is returned.
+ * `stream` is a cudaStream_t (NULL = the library's own stream). */
 int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const double *fix,
                          double *var, double t0, double t1, const mistra_kpp_opts *o,
                          int32_t *ierr, int32_t *stats, double *hexit, double *texit,
@@ -146,7 +148,9 @@ int mistra_kpp_get_kernel(int mech);
 int mistra_kpp_kernel_for(int mech, int64_t ncell);
 int64_t mistra_kpp_launch_count_variant(int variant);
 
-/* Release device workspaces, pinned staging buffers and the library stream. */
+/* Release what the KPP integrators hold on every device they ran on: lane workspaces, on-chip instruction tables,
+ * staging buffers, streams and events.  (The grid caches and scratch buffers of the particle-grid and column
+ * operators - mistra_bins.h, mistra_kon.h, ... - are small and live until the process exits.) */
 int mistra_kpp_finalize(void);
 
 const char *mistra_kpp_last_error(void);
