@@ -85,3 +85,7 @@ extern "C" int mistra_rconst_update(int mech, const mistra_rate_inputs *in, doub
   }
   return 0;
 }
+
+
+// ---- per-layer tables of the liq_parm chain on the host (include/mistra_liq.h)
+#include "liq_host.inc"
