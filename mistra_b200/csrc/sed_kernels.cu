@@ -1,0 +1,516 @@
+// SUBROUTINE sedp / sedl / sedc on the device (include/mistra_sed.h): CUDA kernels + C-ABI entries.  Role in the
+// reference: /root/reference/src/str.f90:2257-2411 (sedp), 2627-2787 (sedl), 2567-2596 (sedc, species loop), with
+// advsed0 / advsed1 (5522-5691) and vterm (2793-2864).
+//
+// Mapping.  Every settling profile - one class (jt, ia) of the spectrum in sedp, one species (l, kc) of the aqueous
+// arrays in sedl - is an independent 1-D advection problem over the levels 1..nf whose flux limiter is a recurrence
+// from the top level down (fm(i-1) needs fm(i), str.f90:5655-5672).  One thread owns one profile: consecutive
+// threads are consecutive classes / species, which are contiguous in memory at every level, so each level is one
+// coalesced row per warp.  The profile psi = field * detw lives in shared memory ([level][thread], conflict-free)
+// for all sub-steps of the time splitting; a sweep keeps the five old values the polynomial fit needs in registers
+// and writes the new value of level i as soon as fm(i-1) is known, so neither the fit coefficients a0..a4 nor the
+// fluxes are stored.  Courant numbers are formed on the way: in sedp from vterm at that level (the reference calls
+// vterm again in every sub-step, str.f90:2364, and so does this kernel - rho_a and eta of the level are tabulated in
+// shared memory), in sedl from the block's table cc(k) of the bin (all threads of a block share the bin, hence the
+// number of sub-steps).  sedp's diagnostics need the classes in the reference's order (a running sum, and x0 carried
+// from one class to the next): the class kernel leaves x0 and a flag per class, sedp_diag_kernel (one block per
+// column) forms x2 in parallel and adds up in order with one thread.
+// Roofline: sedp moves ff once in and once out (2 * 8 B per grid point and level) but executes ~9 IEEE divisions and
+// ~60 other FP64 operations per level, class and sub-step: FP64-bound for populated classes, HBM-bound for the empty
+// ones (a read only).  No FMA contraction (build.py).
+#include "../../include/mistra_sed.h"
+#include "../../include/mistra_kpp.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+int mistra_internal_fail(int code, const std::string &msg);  // kpp_api.cu
+
+namespace {
+
+constexpr int SEDP_T = 128;      // classes per block
+constexpr int SEDL_T = 64;       // species per block
+constexpr int SED_MAXN = 512;
+
+__device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }   // gfortran MIN / MAX
+__device__ __forceinline__ double dmax(double a, double b) { return b > a ? b : a; }
+
+// x / d without the slow path CUDA's division takes for a zero numerator (see difc_kernels.cu): exact for d a
+// positive normal number
+__device__ __forceinline__ double div_pos(double x, double d)
+{
+  const bool z = (((__double2hiint(x) & 0x7fffffff) | __double2loint(x)) == 0) &
+                 ((unsigned)(__double2hiint(d) - 0x00100000) < 0x7fe00000u);
+  double xs = z ? 1.0 : x;
+  asm("" : "+d"(xs));
+  const double q = xs / d;
+  return z ? x : q;
+}
+
+// FUNCTION vterm(a,t,p), str.f90:2793-2864, with rho_a = p/(r0*t) and eta = 3.7957d-06+4.9d-08*t of the level given
+__device__ __forceinline__ double vterm_lev(double a, double t, double p, double rho_a, double eta)
+{
+  const double g = 9.80665, rhow = 1000.0;   // constants.f90
+  const double b0 = -.318657e+1, b1 = .992696e+0, b2 = -.153193e-2, b3 = -.987059e-3, b4 = -.578878e-3,
+               b5 = +.855176e-4, b6 = -.327815e-5;
+  const double c1 = 2.0 * g / 9.0, c2 = 1.26, P0 = 101325, T0 = 293.15, lambda0 = 6.6e-8;
+  const double c3 = c2 * lambda0 * P0 / T0, c4 = 32.0 * g / 3.0;
+  if (a <= 1.e-5) return c1 * a * a * (rhow - rho_a) / eta * (1.0 + c3 * t / (a * p));
+  const double best = c4 * (a * a * a) * (rhow - rho_a) * rho_a / (eta * eta);
+  const double x = log(best);
+  double y = b6 * x + b5;
+  y = y * x + b4;
+  y = y * x + b3;
+  y = y * x + b2;
+  y = y * x + b1;
+  y = y * x + b0;
+  return eta * exp(y) / (2. * rho_a * a);
+}
+
+__device__ __forceinline__ double rho_air(double t, double p)
+{
+  const double gas_const = 8.3144743, M_air = 28.96546e-3;
+  const double r0 = gas_const / M_air;
+  return p / (r0 * t);
+}
+__device__ __forceinline__ double eta_air(double t) { return 3.7957e-06 + 4.9e-08 * t; }
+
+// SUBROUTINE advsed1 (str.f90:5585-5691) on y[0..nf-1] (stride T in shared memory).  cneg(i) = -c(i+1) of the
+// reference (0-based level i), evaluated once per level from the top down.
+template <int T, class CNEG>
+__device__ __forceinline__ void advsed1_dev(int nf, double *y, CNEG cneg)
+{
+#define Y(i) y[(i) * T]
+  double cl = cneg(nf - 2);
+  const double yt = Y(nf - 1), ytm = Y(nf - 2);
+  double fm_up = dmin(yt, cl * (yt - (1.0 - cl) * (yt - ytm) * 0.5));          // fm(nf-1)
+  Y(nf - 1) = yt - fm_up;
+  double clm = cl;
+  double yp2 = 0.0, yp1 = yt, y0 = ytm, ym1 = Y(nf - 3), ym2 = Y(nf - 4);
+  for (int i = nf - 2; i >= 1; --i) {
+    cl = clm;
+    clm = cneg(i - 1);
+    double a0, a1, a2, a3, a4;
+    if (i == 1 || i == nf - 2) {                                              // 5613-5617, 5628-5632
+      a0 = (26.0 * y0 - yp1 - ym1) / 24.0;
+      a1 = (yp1 - ym1) / 16.0;
+      a2 = (yp1 + ym1 - 2.0 * y0) / 48.0;
+      a3 = 0.0;
+      a4 = 0.0;
+    } else {                                                                  // 5619-5626
+      a0 = (9.0 * (yp2 + ym2) - 116.0 * (yp1 + ym1) + 2134.0 * y0) / 1920.0;
+      a1 = (-5.0 * (yp2 - ym2) + 34.0 * (yp1 - ym1)) / 384.0;
+      a2 = (-yp2 + 12.0 * (yp1 + ym1) - 22.0 * y0 - ym2) / 384.0;
+      a3 = (yp2 - 2.0 * (yp1 - ym1) - ym2) / 768.0;
+      a4 = (yp2 - 4.0 * (yp1 + ym1) + 6.0 * y0 + ym2) / 3840.0;
+    }
+    const double x1 = 1.0 - 2.0 * cl;
+    const double x2 = x1 * x1;
+    const double x3 = x1 * x2;
+    const double ymin = dmin(y0, yp1);
+    const double ymax = dmax(y0, yp1);
+    double fmim = dmax(0.0, a0 * cl - a1 * (1.0 - x2) + a2 * (1.0 - x3) - a3 * (1.0 - x1 * x3) + a4 * (1.0 - x2 * x3));
+    fmim = dmin(fmim, y0 - ymin + fm_up);
+    fmim = dmax(fmim, y0 - ymax + fm_up);
+    fmim = dmax(0.0, fmim - (cl - clm) * y0);
+    const double w = div_pos(y0, dmax(fmim + 1.e-15, y0));
+    const double fm_dn = fmim * w;                                            // fm(i-1)
+    Y(i) = y0 - fm_dn + fm_up;
+    fm_up = fm_dn;
+    yp2 = yp1; yp1 = y0; y0 = ym1; ym1 = ym2;
+    ym2 = (i >= 3) ? Y(i - 3) : 0.0;
+  }
+  Y(0) = y0 + fm_up;                                                          // y(1) = y(1) + fm(1)
+#undef Y
+}
+
+// SUBROUTINE advsed0 (str.f90:5522-5579): upstream; c(i) = -cneg(i)
+template <int T, class CNEG>
+__device__ __forceinline__ void advsed0_dev(int nf, double *y, CNEG cneg)
+{
+#define Y(i) y[(i) * T]
+  double ym = Y(0), yc = Y(1);
+  const double c0 = -cneg(0);
+  double fm_prev = -dmin(0.0, c0) * yc, fp_prev = dmax(0.0, c0) * ym;
+  for (int i = 1; i <= nf - 2; ++i) {
+    const double yn = Y(i + 1);
+    const double ci = -cneg(i);
+    const double fm_i = -dmin(0.0, ci) * yn, fp_i = dmax(0.0, ci) * yc;
+    Y(i) = yc - fm_prev + fp_prev + fm_i - fp_i;
+    fm_prev = fm_i; fp_prev = fp_i; ym = yc; yc = yn;
+  }
+#undef Y
+}
+
+// ---- sedp -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEDP_T)
+sedp_class_kernel(mistra_sedp_args a, double *__restrict__ x0c, unsigned char *__restrict__ flag)
+{
+  extern __shared__ double sm[];
+  const int n = a.n, nf = a.nf, row = a.nka * a.nkt;
+  double *s_detw = sm, *s_deta = sm + nf, *s_t = sm + 2 * nf, *s_p = sm + 3 * nf, *s_rho = sm + 4 * nf,
+         *s_eta = sm + 5 * nf, *psi = sm + 6 * nf + threadIdx.x;
+  const size_t col = blockIdx.y;
+  for (int k = threadIdx.x; k < nf; k += SEDP_T) {
+    const double tk = a.t[col * n + k], pk = a.p[col * n + k];
+    s_detw[k] = a.detw[k]; s_deta[k] = a.deta[k]; s_t[k] = tk; s_p[k] = pk;
+    s_rho[k] = rho_air(tk, pk); s_eta[k] = eta_air(tk);
+  }
+  __syncthreads();
+  const int q = blockIdx.x * SEDP_T + threadIdx.x;
+  if (q >= row) return;
+  double *f = a.ff + col * (size_t)n * row + q;
+  const double rqq = a.rq[q], aq = rqq * 1.e-6;
+  double xsum = 0.0;
+#pragma unroll 8
+  for (int k = 1; k < nf; ++k) {                                              // str.f90:2346-2349
+    const double v = f[(size_t)k * row] * s_detw[k];
+    psi[k * SEDP_T] = v;
+    xsum = xsum + v;
+  }
+  const bool run = xsum > 1.e-6;
+  double x0 = 0.0;
+  if (run) {
+    const double ww = -1. * vterm_lev(aq, s_t[nf - 1], s_p[nf - 1], s_rho[nf - 1], s_eta[nf - 1]);
+    const double x3 = -s_deta[1], vdq = a.vd[col * row + q];
+    double dt0 = a.dt;
+    for (int it = 0; dt0 > 0.1 && it < MISTRA_SED_MAXSUB; ++it) {             // 2355-2385
+      const double dtmax = dmin(dt0, x3 / (ww));
+      double c2 = dtmax / s_deta[1] * (-1. * vterm_lev(aq, s_t[1], s_p[1], s_rho[1], s_eta[1]));
+      c2 = dmin(c2, dtmax / s_deta[1] * vdq * (-1.));
+      dt0 = dt0 - dtmax;
+      const double x1 = psi[1 * SEDP_T];
+      psi[0] = x1;
+      auto cneg = [&](int i) -> double {
+        if (i <= 1) return -c2;
+        return -(dtmax / s_deta[i] * (-1. * vterm_lev(aq, s_t[i], s_p[i], s_rho[i], s_eta[i])));
+      };
+      if (rqq < 1.0) advsed0_dev<SEDP_T>(nf, psi, cneg); else advsed1_dev<SEDP_T>(nf, psi, cneg);
+      x0 = x0 + psi[0] - x1;
+    }
+    double last = 0.0;
+    for (int k = 1; k < nf - 1; ++k) {                                        // 2388-2391
+      last = div_pos(psi[k * SEDP_T], s_detw[k]);
+      f[(size_t)k * row] = last;
+    }
+    f[(size_t)(nf - 1) * row] = last;
+  }
+  x0c[col * row + q] = x0;
+  flag[col * row + q] = run ? 1 : 0;
+}
+
+// str.f90:2393-2409: x2 per class with the x0 the reference would hold at that point, then the running sums in the
+// reference's class order.  One block per column; dynamic shared memory: row doubles.
+__global__ void __launch_bounds__(256)
+sedp_diag_kernel(mistra_sedp_args a, const double *__restrict__ x0c, const unsigned char *__restrict__ flag)
+{
+  extern __shared__ double s_x2[];
+  const int row = a.nka * a.nkt, nkt = a.nkt;
+  const size_t col = blockIdx.x;
+  const double *x0 = x0c + col * row;
+  const unsigned char *fl = flag + col * row;
+  const double detw2 = a.detw[1];
+  // every thread owns a contiguous stretch of classes; x0 entering the stretch = that of the last settled class before it
+  const int per = (row + 255) / 256, q0 = threadIdx.x * per, q1 = min(row, q0 + per);
+  double carry = 0.0;
+  for (int q = q0 - 1; q >= 0; --q)
+    if (fl[q]) { carry = x0[q]; break; }
+  for (int q = q0; q < q1; ++q) {
+    if (fl[q]) carry = x0[q];
+    s_x2[q] = carry * a.e[q % nkt] * detw2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double *dg = a.diag + col * 4;
+    double ajs = 0.0, trdep = dg[1], ds1 = dg[2], ds2 = dg[3];
+    const double dt = a.dt;
+    for (int ia = 0; ia < a.nka; ++ia) {
+      const int kwi = a.kw[ia];
+      for (int jt = 0; jt < nkt; ++jt) {
+        const double x2 = s_x2[ia * nkt + jt];
+        ajs = ajs + div_pos(x2, dt);
+        trdep = trdep + x2;
+        if (jt + 1 <= kwi) ds1 = ds1 + x2; else ds2 = ds2 + x2;
+      }
+    }
+    dg[0] = ajs; dg[1] = trdep; dg[2] = ds1; dg[3] = ds2;
+  }
+}
+
+// ---- sedl -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEDL_T)
+sedl_kernel(mistra_sedl_args a, double *__restrict__ s, int jx, int nchunk)
+{
+  extern __shared__ double sm[];
+  const int n = a.n, nf = a.nf, nkc = a.nkc;
+  double *s_detw = sm, *s_cc = sm + nf, *psi = sm + 2 * nf + threadIdx.x;
+  const size_t col = blockIdx.y;
+  const int kc = blockIdx.x / nchunk, l = (blockIdx.x % nchunk) * SEDL_T + threadIdx.x;
+  for (int k = threadIdx.x; k < nf; k += SEDL_T) {                            // str.f90:2691-2701
+    s_detw[k] = a.detw[k];
+    if (k >= 1) {
+      const double tk = a.t[col * n + k], pk = a.p[col * n + k];
+      const double xxx = 0.01;
+      const double x4 = dmax(xxx, 1.e6 * a.rc[(col * n + k) * nkc + kc]);
+      double cc = (-1.0 * vterm_lev(x4 * 1.e-6, tk, pk, rho_air(tk, pk), eta_air(tk))) / a.deta[k];
+      cc = dmin(cc, -1.0 * a.vt[(col * n + k) * nkc + kc] / a.deta[k]);
+      if (k == 1) cc = dmin(cc, -1.0 / a.deta[1] * a.vdm[col * nkc + kc]);
+      s_cc[k] = cc;
+    }
+  }
+  __syncthreads();
+  if (l >= jx) return;
+  const size_t row = (size_t)nkc * jx;
+  double *sl = s + col * (size_t)n * row + (size_t)kc * jx + l;
+#pragma unroll 8
+  for (int k = 1; k < nf; ++k) psi[k * SEDL_T] = sl[(size_t)k * row] * s_detw[k];
+  double dt0 = a.dt, x0 = 0.0;
+  const double xxxt = -.999 / s_cc[1];
+  for (int it = 0; dt0 > 0.1 && it < MISTRA_SED_MAXSUB; ++it) {               // 2708-2720
+    const double dtmax = dmin(dt0, xxxt);
+    dt0 = dt0 - dtmax;
+    const double x1 = psi[1 * SEDL_T];
+    psi[0] = x1;
+    advsed1_dev<SEDL_T>(nf, psi, [&](int i) -> double { return -(s_cc[i < 1 ? 1 : i] * dtmax); });
+    x0 = x0 + psi[0] - x1;
+  }
+  for (int k = 1; k < nf - 1; ++k) sl[(size_t)k * row] = div_pos(psi[k * SEDL_T], s_detw[k]);
+  sl[0] = sl[0] + x0 * a.deta[1];                                             // wet deposition, 2727
+}
+
+// ---- sedc -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+sedc_kernel(mistra_sedc_args a, long long ncol)
+{
+  const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (i >= ncol * a.j1) return;
+  const long long col = i / a.j1;
+  const int j = (int)(i % a.j1);
+  const double Avogadro = 6.022140857e+23, x4 = 1.0;
+  double *lev1 = a.s1 + col * (long long)a.n * a.j1 + j, *lev2 = lev1 + a.j1;
+  const double w = a.vg[j], deta2 = a.deta[1];
+  double s2 = *lev2;
+  if (w >= 1.e-5) {                                                           // str.f90:2591-2594
+    const double s12old = s2;
+    s2 = s2 * exp(-a.dt / deta2 * w);
+    *lev1 = *lev1 + (s12old - s2) * deta2;
+  }
+  *lev2 = s2 + a.es1[j] * x4 * a.dt * 1.e+4 / (a.detw[1] * Avogadro);          // 2596
+}
+
+std::recursive_mutex g_mu;
+std::atomic<long long> g_launches{0};
+struct Scratch { char *p = nullptr; size_t bytes = 0; };
+Scratch g_stage[16], g_work[16];
+bool g_attr[16] = {};
+
+#define CKW(call)                                                                       \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return mistra_internal_fail(e_ == cudaErrorMemoryAllocation ? MISTRA_KPP_ENOMEM   \
+                                  : (e_ == cudaErrorNoDevice ? MISTRA_KPP_ENODEVICE     \
+                                                             : MISTRA_KPP_ECUDA),       \
+                                  std::string(#call) + ": " + cudaGetErrorString(e_));  \
+  } while (0)
+
+int grow(Scratch &sc, size_t bytes)
+{
+  if (sc.bytes >= bytes) return 0;
+  if (sc.p) { CKW(cudaDeviceSynchronize()); cudaFree(sc.p); sc.p = nullptr; sc.bytes = 0; }
+  CKW(cudaMalloc(&sc.p, bytes));
+  sc.bytes = bytes;
+  return 0;
+}
+
+int current_device(int *dev)
+{
+  CKW(cudaGetDevice(dev));
+  if (*dev < 0 || *dev >= 16) return mistra_internal_fail(MISTRA_KPP_ENODEVICE, "device index out of range");
+  if (!g_attr[*dev]) {
+    CKW(cudaFuncSetAttribute(sedp_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    CKW(cudaFuncSetAttribute(sedl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    CKW(cudaFuncSetAttribute(sedp_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    g_attr[*dev] = true;
+  }
+  return 0;
+}
+
+// host-buffer entries: stage `items` into one scratch block, run, copy the outputs back
+struct Item { const void *h; size_t bytes; bool out; void **slot; };
+template <class F>
+int staged(std::vector<Item> &items, cudaStream_t st, F run)
+{
+  int dev = -1;
+  if (int rc = current_device(&dev)) return rc;
+  size_t total = 0;
+  for (auto &it : items) total += (it.bytes + 255) & ~(size_t)255;
+  if (int rc = grow(g_stage[dev], total)) return rc;
+  char *p = g_stage[dev].p;
+  for (auto &it : items) {
+    if (!it.h) { *it.slot = nullptr; continue; }
+    *it.slot = p;
+    CKW(cudaMemcpyAsync(p, it.h, it.bytes, cudaMemcpyHostToDevice, st));
+    p += (it.bytes + 255) & ~(size_t)255;
+  }
+  int rc = run();
+  if (rc) { cudaStreamSynchronize(st); return rc; }
+  for (auto &it : items)
+    if (it.out && it.h) CKW(cudaMemcpyAsync((void *)it.h, *it.slot, it.bytes, cudaMemcpyDeviceToHost, st));
+  CKW(cudaStreamSynchronize(st));
+  return 0;
+}
+
+bool bad_levels(int n, int nf) { return n < 6 || n > SED_MAXN || nf < 6 || nf > n; }
+
+}  // namespace
+
+extern "C" {
+
+int mistra_sedp_device(int64_t ncol, const mistra_sedp_args *d_a, void *stream)
+{
+  if (ncol < 0 || !d_a) return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad arguments");
+  const mistra_sedp_args &a = *d_a;
+  if (bad_levels(a.n, a.nf) || a.nka < 1 || a.nkt < 1 || (int64_t)a.nka * a.nkt > 16000)
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad sizes (6 <= nf <= n <= 512, 1 <= nka * nkt <= 16000)");
+  if (!a.detw || !a.deta || !a.rq || !a.e || !a.kw || (ncol > 0 && (!a.t || !a.p || !a.vd || !a.ff || !a.diag)))
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "null array");
+  if (ncol == 0) return 0;
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  int dev = -1;
+  if (int rc = current_device(&dev)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t row = (size_t)a.nka * a.nkt;
+  const size_t chunk = 32768;                                                 // columns per launch (gridDim.y)
+  if (int rc = grow(g_work[dev], std::min((size_t)ncol, chunk) * row * 9 + 256)) return rc;
+  const size_t smem = ((size_t)6 * a.nf + (size_t)a.nf * SEDP_T) * sizeof(double);
+  for (size_t c0 = 0; c0 < (size_t)ncol; c0 += chunk) {
+    const size_t nc = std::min(chunk, (size_t)ncol - c0);
+    mistra_sedp_args b = a;
+    b.t += c0 * a.n; b.p += c0 * a.n; b.vd += c0 * row; b.ff += c0 * a.n * row; b.diag += c0 * 4;
+    double *x0c = (double *)g_work[dev].p;
+    unsigned char *flag = (unsigned char *)(x0c + nc * row);
+    sedp_class_kernel<<<dim3((unsigned)((row + SEDP_T - 1) / SEDP_T), (unsigned)nc), SEDP_T, smem, st>>>(b, x0c, flag);
+    CKW(cudaGetLastError());
+    sedp_diag_kernel<<<(unsigned)nc, 256, row * sizeof(double), st>>>(b, x0c, flag);
+    CKW(cudaGetLastError());
+    g_launches.fetch_add(2);
+  }
+  return 0;
+}
+
+int mistra_sedp(int64_t ncol, const mistra_sedp_args *a, void *stream)
+{
+  if (ncol < 0 || !a) return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad arguments");
+  if (bad_levels(a->n, a->nf) || a->nka < 1 || a->nkt < 1)
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad sizes (6 <= nf <= n <= 512)");
+  if (!a->detw || !a->deta || !a->rq || !a->e || !a->kw || (ncol > 0 && (!a->t || !a->p || !a->vd || !a->ff || !a->diag)))
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "null array");
+  if (ncol == 0) return 0;
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  const size_t nc = (size_t)ncol, n = a->n, row = (size_t)a->nka * a->nkt;
+  mistra_sedp_args d = *a;
+  std::vector<Item> items = {
+      {a->detw, n * 8, false, (void **)&d.detw}, {a->deta, n * 8, false, (void **)&d.deta},
+      {a->t, nc * n * 8, false, (void **)&d.t}, {a->p, nc * n * 8, false, (void **)&d.p},
+      {a->rq, row * 8, false, (void **)&d.rq}, {a->e, (size_t)a->nkt * 8, false, (void **)&d.e},
+      {a->kw, (size_t)a->nka * 4, false, (void **)&d.kw}, {a->vd, nc * row * 8, false, (void **)&d.vd},
+      {a->ff, nc * n * row * 8, true, (void **)&d.ff}, {a->diag, nc * 4 * 8, true, (void **)&d.diag}};
+  return staged(items, (cudaStream_t)stream, [&] { return mistra_sedp_device(ncol, &d, stream); });
+}
+
+int mistra_sedl_device(int64_t ncol, const mistra_sedl_args *d_a, void *stream)
+{
+  if (ncol < 0 || !d_a) return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad arguments");
+  const mistra_sedl_args &a = *d_a;
+  if (bad_levels(a.n, a.nf) || a.nkc < 1 || a.nkc_l < 0 || a.nkc_l > a.nkc || (a.sl1 && a.j2 < 1) || (a.sion1 && a.j6 < 1))
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad sizes (6 <= nf <= n <= 512, 0 <= nkc_l <= nkc, j2, j6 >= 1)");
+  if (!a.detw || !a.deta || (ncol > 0 && (!a.t || !a.p || !a.rc || !a.vt || !a.vdm)))
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "null array");
+  if (ncol == 0 || a.nkc_l == 0) return 0;
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  int dev = -1;
+  if (int rc = current_device(&dev)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = ((size_t)2 * a.nf + (size_t)a.nf * SEDL_T) * sizeof(double);
+  const size_t chunk = 32768;
+  for (size_t c0 = 0; c0 < (size_t)ncol; c0 += chunk) {
+    const size_t nc = std::min(chunk, (size_t)ncol - c0);
+    mistra_sedl_args b = a;
+    b.t += c0 * a.n; b.p += c0 * a.n; b.rc += c0 * a.n * a.nkc; b.vt += c0 * a.n * a.nkc; b.vdm += c0 * a.nkc;
+    for (int f = 0; f < 2; ++f) {
+      double *s = f ? a.sion1 : a.sl1;
+      const int jx = f ? a.j6 : a.j2;
+      if (!s) continue;
+      const int nchunk = (jx + SEDL_T - 1) / SEDL_T;
+      sedl_kernel<<<dim3((unsigned)(nchunk * a.nkc_l), (unsigned)nc), SEDL_T, smem, st>>>(
+          b, s + c0 * a.n * (size_t)a.nkc * jx, jx, nchunk);
+      CKW(cudaGetLastError());
+      g_launches.fetch_add(1);
+    }
+  }
+  return 0;
+}
+
+int mistra_sedl(int64_t ncol, const mistra_sedl_args *a, void *stream)
+{
+  if (ncol < 0 || !a) return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad arguments");
+  if (bad_levels(a->n, a->nf) || a->nkc < 1 || (a->sl1 && a->j2 < 1) || (a->sion1 && a->j6 < 1))
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad sizes (6 <= nf <= n <= 512, j2, j6 >= 1)");
+  if (!a->detw || !a->deta || (ncol > 0 && (!a->t || !a->p || !a->rc || !a->vt || !a->vdm)))
+    return mistra_internal_fail(MISTRA_KPP_EINVAL, "null array");
+  if (ncol == 0) return 0;
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  const size_t nc = (size_t)ncol, n = a->n, nkc = a->nkc;
+  mistra_sedl_args d = *a;
+  std::vector<Item> items = {
+      {a->detw, n * 8, false, (void **)&d.detw}, {a->deta, n * 8, false, (void **)&d.deta},
+      {a->t, nc * n * 8, false, (void **)&d.t}, {a->p, nc * n * 8, false, (void **)&d.p},
+      {a->rc, nc * n * nkc * 8, false, (void **)&d.rc}, {a->vt, nc * n * nkc * 8, false, (void **)&d.vt},
+      {a->vdm, nc * nkc * 8, false, (void **)&d.vdm},
+      {a->sl1, a->sl1 ? nc * n * nkc * (size_t)a->j2 * 8 : 0, true, (void **)&d.sl1},
+      {a->sion1, a->sion1 ? nc * n * nkc * (size_t)a->j6 * 8 : 0, true, (void **)&d.sion1}};
+  return staged(items, (cudaStream_t)stream, [&] { return mistra_sedl_device(ncol, &d, stream); });
+}
+
+int mistra_sedc_device(int64_t ncol, const mistra_sedc_args *d_a, void *stream)
+{
+  if (ncol < 0 || !d_a) return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad arguments");
+  const mistra_sedc_args &a = *d_a;
+  if (a.n < 2 || a.j1 < 1) return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad sizes (n >= 2, j1 >= 1)");
+  if (!a.detw || !a.deta || !a.vg || !a.es1 || (ncol > 0 && !a.s1)) return mistra_internal_fail(MISTRA_KPP_EINVAL, "null array");
+  if (ncol == 0) return 0;
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  int dev = -1;
+  if (int rc = current_device(&dev)) return rc;
+  const long long tot = (long long)ncol * a.j1;
+  sedc_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, (long long)ncol);
+  CKW(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mistra_sedc(int64_t ncol, const mistra_sedc_args *a, void *stream)
+{
+  if (ncol < 0 || !a) return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad arguments");
+  if (a->n < 2 || a->j1 < 1) return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad sizes (n >= 2, j1 >= 1)");
+  if (!a->detw || !a->deta || !a->vg || !a->es1 || (ncol > 0 && !a->s1)) return mistra_internal_fail(MISTRA_KPP_EINVAL, "null array");
+  if (ncol == 0) return 0;
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  const size_t nc = (size_t)ncol, n = a->n, j1 = a->j1;
+  mistra_sedc_args d = *a;
+  std::vector<Item> items = {
+      {a->detw, n * 8, false, (void **)&d.detw}, {a->deta, n * 8, false, (void **)&d.deta},
+      {a->vg, j1 * 8, false, (void **)&d.vg}, {a->es1, j1 * 8, false, (void **)&d.es1},
+      {a->s1, nc * n * j1 * 8, true, (void **)&d.s1}};
+  return staged(items, (cudaStream_t)stream, [&] { return mistra_sedc_device(ncol, &d, stream); });
+}
+
+int64_t mistra_sed_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"
