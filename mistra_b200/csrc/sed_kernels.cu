@@ -12,9 +12,11 @@
 // fluxes are stored.  Courant numbers are formed on the way: in sedp from vterm at that level (the reference calls
 // vterm again in every sub-step, str.f90:2364, and so does this kernel - rho_a and eta of the level are tabulated in
 // shared memory), in sedl from the block's table cc(k) of the bin (all threads of a block share the bin, hence the
-// number of sub-steps).  sedp's diagnostics need the classes in the reference's order (a running sum, and x0 carried
-// from one class to the next): the class kernel leaves x0 and a flag per class, sedp_diag_kernel (one block per
-// column) forms x2 in parallel and adds up in order with one thread.
+// number of sub-steps).  sedp first finds the classes that hold particles (the others are skipped by the reference,
+// and are the bulk of a real spectrum), lists them by size and hands them to persistent blocks 64 at a time (see
+// "sedp" below).  Its diagnostics need the classes in the reference's order (running sums, and x0 carried from one
+// class to the next): the work kernel leaves x0 per class, sedp_diag_kernel (one block per column) forms x2 in
+// parallel and adds up in order, one thread per sum.
 // Roofline: sedp moves ff once in and once out (2 * 8 B per grid point and level) but executes ~9 IEEE divisions and
 // ~60 other FP64 operations per level, class and sub-step: FP64-bound for populated classes, HBM-bound for the empty
 // ones (a read only).  No FMA contraction (build.py).
@@ -33,7 +35,6 @@ int mistra_internal_fail(int code, const std::string &msg);  // kpp_api.cu
 
 namespace {
 
-constexpr int SEDP_T = 128;      // classes per block
 constexpr int SEDL_T = 64;       // species per block
 constexpr int SED_MAXN = 512;
 
@@ -148,97 +149,198 @@ __device__ __forceinline__ void advsed0_dev(int nf, double *y, CNEG cneg)
 }
 
 // ---- sedp -------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SEDP_T)
-sedp_class_kernel(mistra_sedp_args a, double *__restrict__ x0c, unsigned char *__restrict__ flag)
+// Real spectra populate a few per cent of the 2-D grid, and only those classes settle (column sum > 1e-6,
+// str.f90:2352).  Five launches per batch of columns:
+//   sedp_scan_kernel   streams ff once (coalesced, HBM-bound): column sum of every class -> flag
+//   sedp_list_kernel   per column: the settling classes, listed with the water index jt outermost, so that
+//                      neighbours in the list have similar radii, i.e. the same advection scheme and similar numbers
+//                      of sub-steps (the cost of a class grows with its terminal velocity)
+//   sedp_units_kernel  work units = 64 consecutive list entries of one column; exclusive scan of the units per column
+//   sedp_work_kernel   persistent blocks fetch units from a counter; one thread per settling class
+//   sedp_diag_kernel   the diagnostics in the reference's class order
+constexpr int SEDP_W = 64;       // classes per work unit = threads of the work kernel
+
+__global__ void __launch_bounds__(256)
+sedp_scan_kernel(mistra_sedp_args a, double *__restrict__ x0c, unsigned char *__restrict__ flag)
+{
+  __shared__ double s_detw[SED_MAXN];
+  const int n = a.n, nf = a.nf, row = a.nka * a.nkt;
+  for (int k = threadIdx.x; k < nf; k += 256) s_detw[k] = a.detw[k];
+  __syncthreads();
+  const size_t col = blockIdx.y;
+  const int q = blockIdx.x * 256 + threadIdx.x;
+  if (q >= row) return;
+  const double *f = a.ff + col * (size_t)n * row + q;
+  double xsum = 0.0;
+#pragma unroll 11
+  for (int k = 1; k < nf; ++k) xsum = xsum + f[(size_t)k * row] * s_detw[k];     // str.f90:2346-2349, in level order
+  flag[col * row + q] = xsum > 1.e-6 ? 1 : 0;
+  x0c[col * row + q] = 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+sedp_list_kernel(int nka, int nkt, const unsigned char *__restrict__ flag, unsigned short *__restrict__ list,
+                 int *__restrict__ cnt, int *__restrict__ units)
+{
+  __shared__ int s_w[8], s_base;
+  const int row = nka * nkt, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t col = blockIdx.x;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int p0 = 0; p0 < row; p0 += 256) {
+    const int p = p0 + threadIdx.x;
+    const int jt = p / nka, ia = p - jt * nka, q = ia * nkt + jt;
+    const bool on = p < row && flag[col * row + q] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) s_w[warp] = __popc(m);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_w[w];
+    if (on) list[col * row + off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += s_w[w];
+      s_base += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { cnt[col] = s_base; units[col] = (s_base + SEDP_W - 1) / SEDP_W; }
+}
+
+__global__ void __launch_bounds__(1024)
+sedp_units_kernel(int nc, const int *__restrict__ units, int *__restrict__ unit_off, int *__restrict__ counter)
+{
+  __shared__ int s_w[32], s_run;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_run = 0; *counter = 0; }
+  __syncthreads();
+  for (int base = 0; base < nc; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nc ? units[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    int off = s_run;
+    for (int w = 0; w < warp; ++w) off += s_w[w];
+    if (i < nc) unit_off[i] = off + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_run = off + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) unit_off[nc] = s_run;
+}
+
+__global__ void __launch_bounds__(SEDP_W)
+sedp_work_kernel(mistra_sedp_args a, int nc, const int *__restrict__ unit_off, const unsigned short *__restrict__ list,
+                 const int *__restrict__ cnt, double *__restrict__ x0c, int *__restrict__ counter)
 {
   extern __shared__ double sm[];
+  __shared__ int s_u;
   const int n = a.n, nf = a.nf, row = a.nka * a.nkt;
   double *s_detw = sm, *s_deta = sm + nf, *s_t = sm + 2 * nf, *s_p = sm + 3 * nf, *s_rho = sm + 4 * nf,
          *s_eta = sm + 5 * nf, *psi = sm + 6 * nf + threadIdx.x;
-  const size_t col = blockIdx.y;
-  for (int k = threadIdx.x; k < nf; k += SEDP_T) {
-    const double tk = a.t[col * n + k], pk = a.p[col * n + k];
-    s_detw[k] = a.detw[k]; s_deta[k] = a.deta[k]; s_t[k] = tk; s_p[k] = pk;
-    s_rho[k] = rho_air(tk, pk); s_eta[k] = eta_air(tk);
-  }
-  __syncthreads();
-  const int q = blockIdx.x * SEDP_T + threadIdx.x;
-  if (q >= row) return;
-  double *f = a.ff + col * (size_t)n * row + q;
-  const double rqq = a.rq[q], aq = rqq * 1.e-6;
-  double xsum = 0.0;
-#pragma unroll 8
-  for (int k = 1; k < nf; ++k) {                                              // str.f90:2346-2349
-    const double v = f[(size_t)k * row] * s_detw[k];
-    psi[k * SEDP_T] = v;
-    xsum = xsum + v;
-  }
-  const bool run = xsum > 1.e-6;
-  double x0 = 0.0;
-  if (run) {
+  const int total = unit_off[nc];
+  for (;;) {
+    __syncthreads();                                                          // the unit before is done with the tables
+    if (threadIdx.x == 0) s_u = atomicAdd(counter, 1);
+    __syncthreads();
+    const int u = s_u;
+    if (u >= total) break;
+    int lo = 0, hi = nc;                                                      // last column with unit_off[col] <= u
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (unit_off[mid] <= u) lo = mid; else hi = mid;
+    }
+    const size_t col = lo;
+    const int i = (u - unit_off[lo]) * SEDP_W + threadIdx.x;
+    for (int k = threadIdx.x; k < nf; k += SEDP_W) {
+      const double tk = a.t[col * n + k], pk = a.p[col * n + k];
+      s_detw[k] = a.detw[k]; s_deta[k] = a.deta[k]; s_t[k] = tk; s_p[k] = pk;
+      s_rho[k] = rho_air(tk, pk); s_eta[k] = eta_air(tk);
+    }
+    __syncthreads();
+    if (i >= cnt[col]) continue;
+    const int q = list[col * row + i];
+    double *f = a.ff + col * (size_t)n * row + q;
+    const double rqq = a.rq[q], aq = rqq * 1.e-6;
+#pragma unroll 11
+    for (int k = 1; k < nf; ++k) psi[k * SEDP_W] = f[(size_t)k * row] * s_detw[k];
     const double ww = -1. * vterm_lev(aq, s_t[nf - 1], s_p[nf - 1], s_rho[nf - 1], s_eta[nf - 1]);
     const double x3 = -s_deta[1], vdq = a.vd[col * row + q];
-    double dt0 = a.dt;
-    for (int it = 0; dt0 > 0.1 && it < MISTRA_SED_MAXSUB; ++it) {             // 2355-2385
+    double dt0 = a.dt, x0 = 0.0;
+    for (int it = 0; dt0 > 0.1 && it < MISTRA_SED_MAXSUB; ++it) {             // str.f90:2355-2385
       const double dtmax = dmin(dt0, x3 / (ww));
       double c2 = dtmax / s_deta[1] * (-1. * vterm_lev(aq, s_t[1], s_p[1], s_rho[1], s_eta[1]));
       c2 = dmin(c2, dtmax / s_deta[1] * vdq * (-1.));
       dt0 = dt0 - dtmax;
-      const double x1 = psi[1 * SEDP_T];
+      const double x1 = psi[1 * SEDP_W];
       psi[0] = x1;
-      auto cneg = [&](int i) -> double {
-        if (i <= 1) return -c2;
-        return -(dtmax / s_deta[i] * (-1. * vterm_lev(aq, s_t[i], s_p[i], s_rho[i], s_eta[i])));
+      auto cneg = [&](int lev) -> double {
+        if (lev <= 1) return -c2;
+        return -(dtmax / s_deta[lev] * (-1. * vterm_lev(aq, s_t[lev], s_p[lev], s_rho[lev], s_eta[lev])));
       };
-      if (rqq < 1.0) advsed0_dev<SEDP_T>(nf, psi, cneg); else advsed1_dev<SEDP_T>(nf, psi, cneg);
+      if (rqq < 1.0) advsed0_dev<SEDP_W>(nf, psi, cneg); else advsed1_dev<SEDP_W>(nf, psi, cneg);
       x0 = x0 + psi[0] - x1;
     }
     double last = 0.0;
     for (int k = 1; k < nf - 1; ++k) {                                        // 2388-2391
-      last = div_pos(psi[k * SEDP_T], s_detw[k]);
+      last = div_pos(psi[k * SEDP_W], s_detw[k]);
       f[(size_t)k * row] = last;
     }
     f[(size_t)(nf - 1) * row] = last;
+    x0c[col * row + q] = x0;
   }
-  x0c[col * row + q] = x0;
-  flag[col * row + q] = run ? 1 : 0;
 }
 
-// str.f90:2393-2409: x2 per class with the x0 the reference would hold at that point, then the running sums in the
-// reference's class order.  One block per column; dynamic shared memory: row doubles.
+// str.f90:2393-2409: x2 per class with the x0 the reference would hold at that point (an empty class keeps the x0 of
+// the last settling class before it), then the running sums in the reference's class order - three dependent chains
+// (ajs; trdep; ds1 | ds2), one thread each in three different warps.  One block per column; dynamic shared memory:
+// 2 * row doubles.
 __global__ void __launch_bounds__(256)
 sedp_diag_kernel(mistra_sedp_args a, const double *__restrict__ x0c, const unsigned char *__restrict__ flag)
 {
   extern __shared__ double s_x2[];
   const int row = a.nka * a.nkt, nkt = a.nkt;
+  double *s_d = s_x2 + row;
   const size_t col = blockIdx.x;
   const double *x0 = x0c + col * row;
   const unsigned char *fl = flag + col * row;
-  const double detw2 = a.detw[1];
-  // every thread owns a contiguous stretch of classes; x0 entering the stretch = that of the last settled class before it
+  const double detw2 = a.detw[1], dt = a.dt;
+  // every thread owns a contiguous stretch of classes; x0 entering the stretch = that of the last settling class before it
   const int per = (row + 255) / 256, q0 = threadIdx.x * per, q1 = min(row, q0 + per);
   double carry = 0.0;
-  for (int q = q0 - 1; q >= 0; --q)
+  for (int q = min(q0, row) - 1; q >= 0; --q)
     if (fl[q]) { carry = x0[q]; break; }
   for (int q = q0; q < q1; ++q) {
     if (fl[q]) carry = x0[q];
-    s_x2[q] = carry * a.e[q % nkt] * detw2;
+    const double x2 = carry * a.e[q % nkt] * detw2;
+    s_x2[q] = x2;
+    s_d[q] = div_pos(x2, dt);
   }
   __syncthreads();
+  double *dg = a.diag + col * 4;
   if (threadIdx.x == 0) {
-    double *dg = a.diag + col * 4;
-    double ajs = 0.0, trdep = dg[1], ds1 = dg[2], ds2 = dg[3];
-    const double dt = a.dt;
+    double ajs = 0.0;
+#pragma unroll 4
+    for (int q = 0; q < row; ++q) ajs = ajs + s_d[q];
+    dg[0] = ajs;
+  } else if (threadIdx.x == 32) {
+    double trdep = dg[1];
+#pragma unroll 4
+    for (int q = 0; q < row; ++q) trdep = trdep + s_x2[q];
+    dg[1] = trdep;
+  } else if (threadIdx.x == 64) {
+    double ds1 = dg[2], ds2 = dg[3];
     for (int ia = 0; ia < a.nka; ++ia) {
       const int kwi = a.kw[ia];
-      for (int jt = 0; jt < nkt; ++jt) {
-        const double x2 = s_x2[ia * nkt + jt];
-        ajs = ajs + div_pos(x2, dt);
-        trdep = trdep + x2;
-        if (jt + 1 <= kwi) ds1 = ds1 + x2; else ds2 = ds2 + x2;
-      }
+      const double *x = s_x2 + ia * nkt;
+      for (int jt = 0; jt < nkt; ++jt)
+        if (jt + 1 <= kwi) ds1 = ds1 + x[jt]; else ds2 = ds2 + x[jt];
     }
-    dg[0] = ajs; dg[1] = trdep; dg[2] = ds1; dg[3] = ds2;
+    dg[2] = ds1; dg[3] = ds2;
   }
 }
 
@@ -333,7 +435,7 @@ int current_device(int *dev)
   CKW(cudaGetDevice(dev));
   if (*dev < 0 || *dev >= 16) return mistra_internal_fail(MISTRA_KPP_ENODEVICE, "device index out of range");
   if (!g_attr[*dev]) {
-    CKW(cudaFuncSetAttribute(sedp_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    CKW(cudaFuncSetAttribute(sedp_work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     CKW(cudaFuncSetAttribute(sedl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     CKW(cudaFuncSetAttribute(sedp_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     g_attr[*dev] = true;
@@ -386,20 +488,38 @@ int mistra_sedp_device(int64_t ncol, const mistra_sedp_args *d_a, void *stream)
   if (int rc = current_device(&dev)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t row = (size_t)a.nka * a.nkt;
-  const size_t chunk = 32768;                                                 // columns per launch (gridDim.y)
-  if (int rc = grow(g_work[dev], std::min((size_t)ncol, chunk) * row * 9 + 256)) return rc;
-  const size_t smem = ((size_t)6 * a.nf + (size_t)a.nf * SEDP_T) * sizeof(double);
+  const size_t chunk = 32768;                                                 // columns per batch (gridDim.y)
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t ncm = std::min((size_t)ncol, chunk);
+  const size_t o_flag = up(ncm * row * 8), o_list = o_flag + up(ncm * row), o_cnt = o_list + up(ncm * row * 2),
+               o_units = o_cnt + up(ncm * 4), o_off = o_units + up(ncm * 4), o_ctr = o_off + up((ncm + 1) * 4);
+  if (int rc = grow(g_work[dev], o_ctr + 256)) return rc;
+  char *wb = g_work[dev].p;
+  double *x0c = (double *)wb;
+  unsigned char *flag = (unsigned char *)(wb + o_flag);
+  unsigned short *list = (unsigned short *)(wb + o_list);
+  int *cnt = (int *)(wb + o_cnt), *units = (int *)(wb + o_units), *unit_off = (int *)(wb + o_off), *counter = (int *)(wb + o_ctr);
+  const size_t smem = ((size_t)6 * a.nf + (size_t)a.nf * SEDP_W) * sizeof(double);
+  static int nsm[16] = {};
+  if (!nsm[dev]) CKW(cudaDeviceGetAttribute(&nsm[dev], cudaDevAttrMultiProcessorCount, dev));
+  int per_sm = 1;
+  CKW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sedp_work_kernel, SEDP_W, smem));
+  const unsigned workers = (unsigned)(nsm[dev] * std::max(per_sm, 1));
   for (size_t c0 = 0; c0 < (size_t)ncol; c0 += chunk) {
     const size_t nc = std::min(chunk, (size_t)ncol - c0);
     mistra_sedp_args b = a;
     b.t += c0 * a.n; b.p += c0 * a.n; b.vd += c0 * row; b.ff += c0 * a.n * row; b.diag += c0 * 4;
-    double *x0c = (double *)g_work[dev].p;
-    unsigned char *flag = (unsigned char *)(x0c + nc * row);
-    sedp_class_kernel<<<dim3((unsigned)((row + SEDP_T - 1) / SEDP_T), (unsigned)nc), SEDP_T, smem, st>>>(b, x0c, flag);
+    sedp_scan_kernel<<<dim3((unsigned)((row + 255) / 256), (unsigned)nc), 256, 0, st>>>(b, x0c, flag);
     CKW(cudaGetLastError());
-    sedp_diag_kernel<<<(unsigned)nc, 256, row * sizeof(double), st>>>(b, x0c, flag);
+    sedp_list_kernel<<<(unsigned)nc, 256, 0, st>>>(a.nka, a.nkt, flag, list, cnt, units);
     CKW(cudaGetLastError());
-    g_launches.fetch_add(2);
+    sedp_units_kernel<<<1, 1024, 0, st>>>((int)nc, units, unit_off, counter);
+    CKW(cudaGetLastError());
+    sedp_work_kernel<<<workers, SEDP_W, smem, st>>>(b, (int)nc, unit_off, list, cnt, x0c, counter);
+    CKW(cudaGetLastError());
+    sedp_diag_kernel<<<(unsigned)nc, 256, 2 * row * sizeof(double), st>>>(b, x0c, flag);
+    CKW(cudaGetLastError());
+    g_launches.fetch_add(5);
   }
   return 0;
 }

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 def test_reference_statement_fixtures(cuda_device, kpp):
     n0 = sm.launch_count()
     z, ff, dg, sl, si, s1 = run_fixture(sm.sedp, sm.sedl, sm.sedc)
-    assert sm.launch_count() == n0 + 2 + 2 + 1                       # classes + diagnostics, sl1 + sion1, sedc
+    assert sm.launch_count() == n0 + 5 + 2 + 1                       # sedp (scan, list, units, work, diagnostics), sl1 + sion1, sedc
     assert close(ff, z["ff1"]) and close(dg, z["diag1"])
     small = z["rq"] <= 10.0
     assert np.array_equal(ff[:, :, small], z["ff1"][:, :, small])

@@ -2,4 +2,4 @@ cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_sed.py -m gpu -q -x > gpurun_out/r02_sed_tests.log 2>&1; echo "tests rc=$?"; tail -15 gpurun_out/r02_sed_tests.log
 timeout 300 python tools/sed_bench.py 256 > gpurun_out/r02_sed_bench.txt 2>&1; cat gpurun_out/r02_sed_bench.txt
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:sed -c 6 -o gpurun_out/r02_sed --force-overwrite python tools/sed_bench.py 64 > gpurun_out/r02_sed_ncu.log 2>&1; tail -3 gpurun_out/r02_sed_ncu.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"sedp_work|sedp_scan|sedp_diag|sedl" -c 8 -o gpurun_out/r02_sed --force-overwrite python tools/sed_bench.py 64 > gpurun_out/r02_sed_ncu.log 2>&1; tail -3 gpurun_out/r02_sed_ncu.log
