@@ -1051,6 +1051,61 @@ def run_next_rows_leg(args, dev, world, rank, barrier):
                                        "sample": "%d x %d columns, OpenMP over columns (includes a copy of the arrays), "
                                                  "%.1f s" % (reps, m, dt)}
     del dd, ffp, fsp, rho
+    # ---- sedp / sedl: gravitational settling of the spectrum and of the aqueous species (row N4, the rest) ----
+    from mistra_b200 import kon as konm, sed as sedm
+    from oracle import sed_oracle as sdo
+    ncs, nfl = max(1, ncol // 8), 100                              # 250 columns: 1.5 GB of ff
+    sg = konm.kon_grid()
+    sd = sedm.synthetic_columns(sg, ncs, n=nlev, nf=nfl, seed=20261018 + rank)
+    sgd = dict(nka=sg["nka"], nkt=sg["nkt"], rq=t(sg["rq"]), e=t(sg["e"]), kw=t(np.asarray(sg["kw"], dtype=np.int32)))
+    sv = {k: t(v) for k, v in sd.items()}
+    sk = {k: sv[k].clone() for k in ("ff", "diag", "sl1", "sion1")}
+    settle = float(((sd["ff"][:, 1:nfl] * sd["detw"][None, 1:nfl, None, None]).sum(axis=1) > 1e-6).mean())
+    l0 = sedm.launch_count()
+    ms = timeit(lambda: sedm.sedp_device(sgd, 10.0, nfl, sv["detw"], sv["deta"], sv["t"], sv["p"], sv["vd"], sv["ff"], sv["diag"]),
+                restore=lambda: (sv["ff"].copy_(sk["ff"]), sv["diag"].copy_(sk["diag"])))
+    by = ncs * (nfl - 1) * 4900 * 8 * (1.0 + 2.0 * settle)
+    res["sedp"] = {"metric": "sedp_columns_per_s", "value": ncs * world / (ms * 1e-3), "unit": "columns/s",
+                   "columns_per_gpu": ncs, "levels": nfl, "settling_classes": settle, "ms_per_step": ms,
+                   "gpu_launches": int(sedm.launch_count() - l0),
+                   "roofline": {"bound": "hbm", "kernel": "sedp_scan_kernel + sedp_work_kernel", "achieved": by / (ms * 1e-3) * 1e-9,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"],
+                                "peak_source": peak_src, "traffic": None,
+                                "note": "algorithmic bytes = every class and level 2..nf read once for the column sums, the "
+                                        "settling classes (%.1f %%) read once more and written once; their ~270 FP64 "
+                                        "instructions per level and sub-step (six IEEE divisions) make the work kernel "
+                                        "latency / FP64-bound" % (100 * settle)}}
+    l0 = sedm.launch_count()
+    ms = timeit(lambda: sedm.sedl_device(10.0, nfl, 4, sv["detw"], sv["deta"], sv["t"], sv["p"], sv["rc"], sv["vt"], sv["vdm"],
+                                         sv["sl1"], sv["sion1"]),
+                restore=lambda: (sv["sl1"].copy_(sk["sl1"]), sv["sion1"].copy_(sk["sion1"])))
+    by = ncs * (nfl - 1) * 4 * (121 + 55) * 8 * 2
+    res["sedl"] = {"metric": "sedl_columns_per_s", "value": ncs * world / (ms * 1e-3), "unit": "columns/s",
+                   "columns_per_gpu": ncs, "levels": nfl, "profiles_per_column": 4 * (121 + 55), "ms_per_step": ms,
+                   "gpu_launches": int(sedm.launch_count() - l0),
+                   "roofline": {"bound": "hbm", "kernel": "sedl_kernel", "achieved": by / (ms * 1e-3) * 1e-9,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"],
+                                "peak_source": peak_src, "traffic": None,
+                                "note": "algorithmic bytes = levels 2..nf of sl1 and sion1 read and written once; every profile "
+                                        "runs advsed1 (six IEEE divisions per level and sub-step): FP64 / latency-bound"}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        m = min(ncs, 16)
+        reps, t1 = 0, time.perf_counter()
+        while time.perf_counter() - t1 < 3.0:
+            sdo.sedp(sg, 10.0, nfl, sd["detw"], sd["deta"], sd["t"][:m], sd["p"][:m], sd["vd"][:m], sd["ff"][:m], sd["diag"][:m])
+            reps += 1
+        dt = time.perf_counter() - t1
+        res["sedp"]["cpu_baseline"] = {"value": m * reps / dt, "unit": "columns/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": "%d x %d columns, OpenMP over columns (includes a copy of ff), %.1f s" % (reps, m, dt)}
+        reps, t1 = 0, time.perf_counter()
+        while time.perf_counter() - t1 < 3.0:
+            for arr in (sd["sl1"], sd["sion1"]):
+                sdo.sedl(10.0, nfl, 4, sd["detw"], sd["deta"], sd["t"][:m], sd["p"][:m], sd["rc"][:m], sd["vt"][:m], sd["vdm"][:m], arr[:m])
+            reps += 1
+        dt = time.perf_counter() - t1
+        res["sedl"]["cpu_baseline"] = {"value": m * reps / dt, "unit": "columns/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": "%d x %d columns, OpenMP over columns, %.1f s" % (reps, m, dt)}
+    del sv, sk, sd
     # ---- gather / scatter halves of aer_drive on device-resident model arrays (rows a14 / a15) ----
     from mistra_b200 import drive
     from mistra_b200.mechgen import mech as mechmod
