@@ -29,11 +29,11 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", HOSTCXX]
 
 UNITS = ["kpp_mech_g.cu", "kpp_mech_a.cu", "kpp_mech_t.cu", "kpp_onchip_g.cu", "kpp_onchip_a.cu", "kpp_api.cu", "bins_kernels.cu",
-         "kon_kernels.cu", "konc_kernels.cu", "cwrc_kernels.cu", "fastkmt_kernels.cu", "difc_kernels.cu", "drive_kernels.cu", "rconst_kernels.cu", "liq_kernels.cu", "sed_kernels.cu", "_gen/kpp_names.cpp",
+         "kon_kernels.cu", "konc_kernels.cu", "cwrc_kernels.cu", "fastkmt_kernels.cu", "difc_kernels.cu", "drive_kernels.cu", "rconst_kernels.cu", "liq_kernels.cu", "sed_kernels.cu", "driver_kernels.cu", "_gen/kpp_names.cpp",
          "_gen/onchip_tables_g_%(v)s.cpp", "_gen/onchip_tables_a_%(v)s.cpp"]
 # per-unit flags: the condensation kernel keeps the reference's unfused arithmetic
 UNIT_FLAGS = {"kon_kernels.cu": ["-fmad=false"], "konc_kernels.cu": ["-fmad=false"], "cwrc_kernels.cu": ["-fmad=false"], "fastkmt_kernels.cu": ["-fmad=false"], "difc_kernels.cu": ["-fmad=false"], "drive_kernels.cu": ["-fmad=false"],
-              "rconst_kernels.cu": ["-fmad=false"], "liq_kernels.cu": ["-fmad=false"], "sed_kernels.cu": ["-fmad=false"]}
+              "rconst_kernels.cu": ["-fmad=false"], "liq_kernels.cu": ["-fmad=false"], "sed_kernels.cu": ["-fmad=false"], "driver_kernels.cu": ["-fmad=false"]}
 
 
 def _hash(paths, extra):
@@ -62,6 +62,8 @@ def _deps(unit):
         deps.append(os.path.join(ROOT, "include", "mistra_difc.h"))
     if unit.startswith("drive_"):
         deps.append(os.path.join(ROOT, "include", "mistra_drive.h"))
+    if unit.startswith("driver_"):
+        deps.append(os.path.join(ROOT, "include", "mistra_driver.h"))
     if unit.startswith("sed_"):
         deps.append(os.path.join(ROOT, "include", "mistra_sed.h"))
     if unit.startswith("liq_"):

@@ -93,12 +93,14 @@ def split_top(s):
 
 def pyexpr(e):
     e = re.sub(r"\b(\w+)\s*\*\*\s*3\b", r"(\1*\1*\1)", e)         # gfortran: x**3 -> x*x*x
-    return expr(e)
+    e = expr(e)
+    return e.replace(".true.", " True ").replace(".false.", " False ")
 
 
-def translate(first, last, name=None, args=(), arrays=(), result=None, commons=()):
-    """Lines first..last (1-based, inclusive) of str.f90 -> Python source.  name=None: module-level statements."""
-    text = open(os.path.join(REF, "str.f90"), errors="replace").read().split("\n")[first - 1:last]
+def translate(first, last, name=None, args=(), arrays=(), result=None, commons=(), fname="str.f90"):
+    """Lines first..last (1-based, inclusive) of a reference source -> Python source.  name=None: module-level
+    statements."""
+    text = open(os.path.join(REF, fname), errors="replace").read().split("\n")[first - 1:last]
     body = logical_lines(text)
     out, ind = [], 0
     known = set(arrays)
@@ -135,6 +137,9 @@ def translate(first, last, name=None, args=(), arrays=(), result=None, commons=(
                 rhs = st[j + 1:].lstrip()
                 assert rhs.startswith("="), s
                 assert lhs in known, ("assignment to an undeclared array", s)
+                if st[i + 1:j].strip() == ":":                           # whole-array assignment  a(:) = scalar
+                    emit("%s.a[...] = %s" % (lhs, pyexpr(rhs[1:])))
+                    return
                 emit("%s.set((%s,), %s)" % (lhs, pyexpr(st[i + 1:j]), pyexpr(rhs[1:])))
             else:
                 emit("%s = %s" % ("_ret" if lhs == result else lhs, pyexpr(m.group(3))))

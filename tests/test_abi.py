@@ -32,6 +32,7 @@ def declared_functions(header):
                                         ("mistra_kpp_rates.h", "libmistra_kpp.so"),
                                         ("mistra_liq.h", "libmistra_kpp.so"),
                                         ("mistra_sed.h", "libmistra_kpp.so"),
+                                        ("mistra_driver.h", "libmistra_kpp.so"),
                                         ("mistra_rconst.h", "libmistra_rconst.so")])
 def test_library_exports_every_declared_symbol(kpp, header, lib):
     L = C.CDLL(os.path.join(ROOT, "mistra_b200", lib))
