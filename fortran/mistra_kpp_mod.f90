@@ -261,3 +261,80 @@ module mistra_drive_mod
      end function mistra_drive_scatter_device
   end interface
 end module mistra_drive_mod
+
+! mistra_sed_mod - ISO_C_BINDING interface of include/mistra_sed.h: SUBROUTINE sedp (str.f90:2257-2411),
+! sedl (2627-2787) and the species loop of sedc (2567-2596) in place; ncol = 1 for the reference's single column.
+module mistra_sed_mod
+  use, intrinsic :: iso_c_binding
+  implicit none
+  type, bind(C) :: mistra_sedp_args
+     integer(c_int32_t) :: n, nf, nka, nkt
+     real(c_double) :: dt
+     type(c_ptr) :: detw, deta, t, p, rq, e, kw, vd, ff, diag
+  end type mistra_sedp_args
+  type, bind(C) :: mistra_sedl_args
+     integer(c_int32_t) :: n, nf, nkc, nkc_l, j2, j6
+     real(c_double) :: dt
+     type(c_ptr) :: detw, deta, t, p, rc, vt, vdm, sl1, sion1
+  end type mistra_sedl_args
+  type, bind(C) :: mistra_sedc_args
+     integer(c_int32_t) :: n, j1
+     real(c_double) :: dt
+     type(c_ptr) :: detw, deta, vg, es1, s1
+  end type mistra_sedc_args
+  interface
+     function mistra_sedp(ncol, a, stream) result(rc) bind(C, name="mistra_sedp")
+       import :: c_int, c_int64_t, c_ptr, mistra_sedp_args
+       integer(c_int64_t), value :: ncol
+       type(mistra_sedp_args), intent(in) :: a
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_sedp
+     function mistra_sedl(ncol, a, stream) result(rc) bind(C, name="mistra_sedl")
+       import :: c_int, c_int64_t, c_ptr, mistra_sedl_args
+       integer(c_int64_t), value :: ncol
+       type(mistra_sedl_args), intent(in) :: a
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_sedl
+     function mistra_sedc(ncol, a, stream) result(rc) bind(C, name="mistra_sedc")
+       import :: c_int, c_int64_t, c_ptr, mistra_sedc_args
+       integer(c_int64_t), value :: ncol
+       type(mistra_sedc_args), intent(in) :: a
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_sedc
+  end interface
+end module mistra_sed_mod
+
+! mistra_driver_mod - ISO_C_BINDING interface of include/mistra_driver.h: the layer loop of kpp_driver
+! (kpp.f90:4305-4470) for an ensemble of columns: per-layer scalars, switches and the layers sorted by mechanism.
+module mistra_driver_mod
+  use, intrinsic :: iso_c_binding
+  implicit none
+  type, bind(C) :: mistra_driver_args
+     integer(c_int32_t) :: n, nf, nkc, nphrxn
+     integer(c_int32_t) :: halo, iod, lpBuys13_0D, neula
+     integer(c_int32_t) :: box, n_bl
+     integer(c_int32_t) :: kinv, nadv, j1, j5
+     real(c_double) :: dt_ch
+     type(c_ptr) :: u0, t, p, rho, cm3, am3, xm1, conv2, cm, cloud, photol_j, adv_row, xadv, s1, s3
+     type(c_ptr) :: cb1, scal, ph_rat, air, h2o, cvv, mech, layers, count
+  end type mistra_driver_args
+  interface
+     function mistra_driver_layers(ncol, a, stream) result(rc) bind(C, name="mistra_driver_layers")
+       import :: c_int, c_int64_t, c_ptr, mistra_driver_args
+       integer(c_int64_t), value :: ncol
+       type(mistra_driver_args), intent(in) :: a
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_driver_layers
+     function mistra_driver_layers_device(ncol, a, stream) result(rc) bind(C, name="mistra_driver_layers_device")
+       import :: c_int, c_int64_t, c_ptr, mistra_driver_args
+       integer(c_int64_t), value :: ncol
+       type(mistra_driver_args), intent(in) :: a
+       type(c_ptr), value :: stream
+       integer(c_int) :: rc
+     end function mistra_driver_layers_device
+  end interface
+end module mistra_driver_mod
