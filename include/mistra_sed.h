@@ -23,7 +23,8 @@
  *   sl1 [ncol][n][nkc][j2], sion1 [ncol][n][nkc][j6]   COMMON /blck17/   IN/OUT, levels 1 .. nf-1, bins 1 .. nkc_l
  *   s1 [ncol][n][j1]         gas_common     IN/OUT, levels 1 and 2
  *   diag [ncol][4]           ajs (OUT), trdep, ds1, ds2 (IN/OUT)   COMMON /cb47/
- * Numerics: binary64, the reference's expressions and operation order, no FMA contraction, IEEE division; every
+ * Numerics: binary64, the reference's expressions and operation order, no FMA contraction, IEEE division (advsed1's
+ * divisions by constants through an equivalent correctly rounded sequence, see mistra_sed_divc_selftest); every
  * profile is a sequential recurrence in the level index evaluated by one thread, the diagnostics are summed over the
  * classes in the reference's order: results are bit-identical to the reference order wherever no exp / log enters
  * (advsed0 / advsed1 themselves, vterm below 10 um radius, hence sedl / sedp of all but large drops); vterm of large
@@ -78,6 +79,13 @@ typedef struct mistra_sedc_args {
 
 int mistra_sedc(int64_t ncol, const mistra_sedc_args *a, void *stream);
 int mistra_sedc_device(int64_t ncol, const mistra_sedc_args *d_a, void *stream);
+
+/* Diagnostic: advsed1's divisions by 24, 48, 1920, 384, 768, 3840 are evaluated on the device as multiply + two FMAs
+ * (correctly rounded by Markstein's theorem inside an exponent window, the IEEE division outside it).  This compares
+ * that sequence with the IEEE division bit for bit on n pseudo-random and structured arguments (all exponents incl.
+ * denormals / Inf / NaN, exactly divisible significands, significands of all ones) and returns the number of differing
+ * results in *mismatches (expected 0).  Synchronous. */
+int mistra_sed_divc_selftest(int64_t n, uint64_t seed, int64_t *mismatches);
 
 /* launches of the three routines */
 int64_t mistra_sed_launch_count(void);

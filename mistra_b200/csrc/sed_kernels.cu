@@ -17,8 +17,8 @@
 // "sedp" below).  Its diagnostics need the classes in the reference's order (running sums, and x0 carried from one
 // class to the next): the work kernel leaves x0 per class, sedp_diag_kernel (one block per column) forms x2 in
 // parallel and adds up in order, one thread per sum.
-// Roofline: sedp moves ff once in and once out (2 * 8 B per grid point and level) but executes ~9 IEEE divisions and
-// ~60 other FP64 operations per level, class and sub-step: FP64-bound for populated classes, HBM-bound for the empty
+// Roofline: sedp moves ff once in and once out (2 * 8 B per grid point and level) but executes ~4 IEEE divisions, five
+// exact divisions by constants (div_const) and ~60 other FP64 operations per level, class and sub-step: FP64-bound for populated classes, HBM-bound for the empty
 // ones (a read only).  No FMA contraction (build.py).
 #include "../../include/mistra_sed.h"
 #include "../../include/mistra_kpp.h"
@@ -51,6 +51,30 @@ __device__ __forceinline__ double div_pos(double x, double d)
   asm("" : "+d"(xs));
   const double q = xs / d;
   return z ? x : q;
+}
+
+// x / (D * 2^K) for D = 3 or 15, correctly rounded, without a division: with r = RN(1 / D) * 2^-K (the scaling is exact)
+// q0 = RN(x * r) is within one ulp of the quotient, e = x - q0 * d is exact (one FMA), and RN(q0 + e * r) is the
+// correctly rounded quotient (Markstein's theorem: r is the correctly rounded reciprocal of a divisor whose significand
+// is not all ones, q0 a faithful quotient).  The theorem needs normal numbers throughout, hence the exponent window
+// 2^-895 <= |x| < 2^897; everything else (zero, denormals, huge values, Inf / NaN) takes the zero shortcut or the IEEE
+// division.  advsed1 divides by 24, 48, 1920, 384, 768 and 3840 at every level (str.f90:5613-5632): five of the six
+// divisions of a level.  mistra_sed_divc_selftest compares it with the division on the device.
+template <int D, int K>
+__device__ __forceinline__ double div_const(double x)
+{
+  static_assert(D == 3 || D == 15, "divisor");
+  const double d = (double)D * (double)(1 << K);
+  const double r = __longlong_as_double(D == 3 ? 0x3FD5555555555555LL : 0x3FB1111111111111LL) * (1.0 / (double)(1 << K));
+  const int hi = __double2hiint(x);
+  const unsigned ex = ((unsigned)hi >> 20) & 0x7ffu;
+  if (ex - 128u < 1792u) {
+    const double q0 = __dmul_rn(x, r);
+    const double e = __fma_rn(-q0, d, x);
+    return __fma_rn(e, r, q0);
+  }
+  if (((hi & 0x7fffffff) | __double2loint(x)) == 0) return x;
+  return x / d;
 }
 
 // FUNCTION vterm(a,t,p), str.f90:2793-2864, with rho_a = p/(r0*t) and eta = 3.7957d-06+4.9d-08*t of the level given
@@ -98,17 +122,17 @@ __device__ __forceinline__ void advsed1_dev(int nf, double *y, CNEG cneg)
     clm = cneg(i - 1);
     double a0, a1, a2, a3, a4;
     if (i == 1 || i == nf - 2) {                                              // 5613-5617, 5628-5632
-      a0 = (26.0 * y0 - yp1 - ym1) / 24.0;
+      a0 = div_const<3, 3>(26.0 * y0 - yp1 - ym1);
       a1 = (yp1 - ym1) / 16.0;
-      a2 = (yp1 + ym1 - 2.0 * y0) / 48.0;
+      a2 = div_const<3, 4>(yp1 + ym1 - 2.0 * y0);
       a3 = 0.0;
       a4 = 0.0;
     } else {                                                                  // 5619-5626
-      a0 = (9.0 * (yp2 + ym2) - 116.0 * (yp1 + ym1) + 2134.0 * y0) / 1920.0;
-      a1 = (-5.0 * (yp2 - ym2) + 34.0 * (yp1 - ym1)) / 384.0;
-      a2 = (-yp2 + 12.0 * (yp1 + ym1) - 22.0 * y0 - ym2) / 384.0;
-      a3 = (yp2 - 2.0 * (yp1 - ym1) - ym2) / 768.0;
-      a4 = (yp2 - 4.0 * (yp1 + ym1) + 6.0 * y0 + ym2) / 3840.0;
+      a0 = div_const<15, 7>(9.0 * (yp2 + ym2) - 116.0 * (yp1 + ym1) + 2134.0 * y0);
+      a1 = div_const<3, 7>(-5.0 * (yp2 - ym2) + 34.0 * (yp1 - ym1));
+      a2 = div_const<3, 7>(-yp2 + 12.0 * (yp1 + ym1) - 22.0 * y0 - ym2);
+      a3 = div_const<3, 8>(yp2 - 2.0 * (yp1 - ym1) - ym2);
+      a4 = div_const<15, 8>(yp2 - 4.0 * (yp1 + ym1) + 6.0 * y0 + ym2);
     }
     const double x1 = 1.0 - 2.0 * cl;
     const double x2 = x1 * x1;
@@ -405,6 +429,38 @@ sedc_kernel(mistra_sedc_args a, long long ncol)
   *lev2 = s2 + a.es1[j] * x4 * a.dt * 1.e+4 / (a.detw[1] * Avogadro);          // 2596
 }
 
+// ---- self-test of div_const against the IEEE division -------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+  z += 0x9E3779B97F4A7C15ull; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+template <int D, int K>
+__device__ __forceinline__ int divc_bad(double x)
+{
+  const double a = div_const<D, K>(x), b = x / ((double)D * (double)(1 << K));
+  return (__double_as_longlong(a) != __double_as_longlong(b) && !(a == 0.0 && b == 0.0) && !(a != a && b != b)) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256)
+divc_selftest_kernel(long long n, unsigned long long seed, unsigned long long *__restrict__ bad)
+{
+  int mine = 0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const unsigned long long h = mix64(seed + (unsigned long long)i), g = mix64(h);
+    // sign | exponent (every value incl. denormals, Inf, NaN in one sample of 16; else 2^-60 .. 2^60) | significand
+    // (random; in one sample of 8 a multiple of the divisors with few trailing bits, the exactly representable quotients;
+    // in one of 8 all ones or all zeros but the last bits)
+    unsigned long long ex = (g & 15u) == 0 ? ((g >> 8) & 0x7ffull) : 963ull + ((g >> 8) % 121ull);
+    unsigned long long man = h & 0xFFFFFFFFFFFFFull;
+    const unsigned sel = (unsigned)(g >> 24) & 7u;
+    if (sel == 0) man = ((h >> 20) * 15ull) & 0xFFFFFFFFFFFFFull;
+    if (sel == 1) man = (g >> 32) & 1 ? 0xFFFFFFFFFFFFFull - (h & 7ull) : (h & 7ull);
+    const double x = __longlong_as_double((long long)(((g >> 63) << 63) | (ex << 52) | man));
+    mine += divc_bad<3, 3>(x) + divc_bad<3, 4>(x) + divc_bad<15, 7>(x) + divc_bad<3, 7>(x) + divc_bad<3, 8>(x) + divc_bad<15, 8>(x);
+  }
+  if (mine) atomicAdd(bad, (unsigned long long)mine);
+}
+
 std::recursive_mutex g_mu;
 std::atomic<long long> g_launches{0};
 struct Scratch { char *p = nullptr; size_t bytes = 0; };
@@ -629,6 +685,23 @@ int mistra_sedc(int64_t ncol, const mistra_sedc_args *a, void *stream)
       {a->vg, j1 * 8, false, (void **)&d.vg}, {a->es1, j1 * 8, false, (void **)&d.es1},
       {a->s1, nc * n * j1 * 8, true, (void **)&d.s1}};
   return staged(items, (cudaStream_t)stream, [&] { return mistra_sedc_device(ncol, &d, stream); });
+}
+
+int mistra_sed_divc_selftest(int64_t n, uint64_t seed, int64_t *mismatches)
+{
+  if (n < 0 || !mismatches) return mistra_internal_fail(MISTRA_KPP_EINVAL, "bad arguments");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  int dev = -1;
+  if (int rc = current_device(&dev)) return rc;
+  if (int rc = grow(g_work[dev], 256)) return rc;
+  unsigned long long *bad = (unsigned long long *)g_work[dev].p;
+  CKW(cudaMemset(bad, 0, sizeof(*bad)));
+  divc_selftest_kernel<<<148 * 8, 256>>>((long long)n, (unsigned long long)seed, bad);
+  CKW(cudaGetLastError());
+  unsigned long long h = 0;
+  CKW(cudaMemcpy(&h, bad, sizeof(h), cudaMemcpyDeviceToHost));
+  *mismatches = (int64_t)h;
+  return 0;
 }
 
 int64_t mistra_sed_launch_count(void) { return g_launches.load(); }

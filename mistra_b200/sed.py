@@ -32,6 +32,7 @@ def _lib():
         getattr(L, "mistra_%s" % name).argtypes = [C.c_int64, C.POINTER(cls), C.c_void_p]
         getattr(L, "mistra_%s_device" % name).argtypes = [C.c_int64, C.POINTER(cls), C.c_void_p]
     L.mistra_sed_launch_count.restype = C.c_int64
+    L.mistra_sed_divc_selftest.argtypes = [C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
     return L
 
 
@@ -187,6 +188,15 @@ def sedc_device(dt, detw, deta, vg, es1, s1, stream=None):
     if stream is None:
         stream = torch.cuda.current_stream().cuda_stream
     kpp._check(L, L.mistra_sedc_device(ncol, C.byref(a), C.c_void_p(stream)))
+
+
+def divc_selftest(n, seed=1):
+    """Number of arguments (of n) for which advsed1's multiply-and-correct divisions by constants differ from the IEEE
+    division on the device (expected 0)."""
+    L = _lib()
+    bad = C.c_int64(-1)
+    kpp._check(L, L.mistra_sed_divc_selftest(int(n), int(seed), C.byref(bad)))
+    return int(bad.value)
 
 
 def launch_count():

@@ -22,6 +22,14 @@ def test_reference_statement_fixtures(cuda_device, kpp):
     assert close(sl, z["sl1"]) and close(si, z["si1"]) and close(s1, z["sedc_s1"])
 
 
+def test_divisions_by_constants_equal_the_ieee_division(cuda_device, kpp):
+    """advsed1's /24, /48, /1920, /384, /768, /3840 as multiply + two FMAs: 6 x 2^28 comparisons with the division on the
+    device, incl. denormals, Inf / NaN, exactly divisible and all-ones significands."""
+    for seed in (1, 2):
+        assert sm.divc_selftest(1 << 28, seed) == 0
+    assert sm.divc_selftest(0) == 0
+
+
 @pytest.mark.parametrize("ncol,seed,n,nf,dt", [(6, 11, 150, 100, 10.0), (3, 12, 150, 100, 60.0), (2, 13, 40, 33, 10.0)])
 def test_sedp_vs_oracle(cuda_device, kpp, ncol, seed, n, nf, dt):
     g = kon.kon_grid()
