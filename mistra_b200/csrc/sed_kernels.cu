@@ -4,22 +4,25 @@
 //
 // Mapping.  Every settling profile - one class (jt, ia) of the spectrum in sedp, one species (l, kc) of the aqueous
 // arrays in sedl - is an independent 1-D advection problem over the levels 1..nf whose flux limiter is a recurrence
-// from the top level down (fm(i-1) needs fm(i), str.f90:5655-5672).  One thread owns one profile: consecutive
-// threads are consecutive classes / species, which are contiguous in memory at every level, so each level is one
-// coalesced row per warp.  The profile psi = field * detw lives in shared memory ([level][thread], conflict-free)
-// for all sub-steps of the time splitting; a sweep keeps the five old values the polynomial fit needs in registers
-// and writes the new value of level i as soon as fm(i-1) is known, so neither the fit coefficients a0..a4 nor the
-// fluxes are stored.  Courant numbers are formed on the way: in sedp from vterm at that level (the reference calls
-// vterm again in every sub-step, str.f90:2364, and so does this kernel - rho_a and eta of the level are tabulated in
-// shared memory), in sedl from the block's table cc(k) of the bin (all threads of a block share the bin, hence the
-// number of sub-steps).  sedp first finds the classes that hold particles (the others are skipped by the reference,
-// and are the bulk of a real spectrum), lists them by size and hands them to persistent blocks 64 at a time (see
-// "sedp" below).  Its diagnostics need the classes in the reference's order (running sums, and x0 carried from one
-// class to the next): the work kernel leaves x0 per class, sedp_diag_kernel (one block per column) forms x2 in
-// parallel and adds up in order, one thread per sum.
-// Roofline: sedp moves ff once in and once out (2 * 8 B per grid point and level) but executes ~4 IEEE divisions, five
-// exact divisions by constants (div_const) and ~60 other FP64 operations per level, class and sub-step: FP64-bound for populated classes, HBM-bound for the empty
-// ones (a read only).  No FMA contraction (build.py).
+// from the top level down (fm(i-1) needs fm(i), str.f90:5655-5672), repeated for a data-dependent number of
+// sub-steps.  One thread owns one profile; consecutive threads are consecutive species (sedl: one coalesced row per
+// warp and level) or neighbouring settling classes (sedp).  A pass works IN PLACE on the profile in global memory:
+// the five old values the polynomial fit needs slide through registers, the values entering that window are loaded
+// four levels at a time and one chunk ahead of their use, and the new value of level i is stored as soon as fm(i-1)
+// is known - neither psi nor the fit coefficients a0..a4 nor the fluxes are kept anywhere else, so the number of
+// resident warps is bounded by registers only (the first version kept psi in shared memory: 800 B per thread,
+// 8 warps per SM).  The first pass reads ff * detw, the last one writes psi / detw, passes in between leave psi itself
+// in the array (profiles with one pass - almost all - touch each level once).  Courant numbers are formed on the way:
+// in sedp from vterm at that level (the reference calls vterm again in every sub-step, str.f90:2364, and so does this
+// kernel - rho_a and eta of the level are tabulated in shared memory), in sedl from the block's table cc(k) of the
+// bin (all threads of a block share the bin, hence the number of sub-steps).  sedp first finds the classes that hold
+// particles (the others are skipped by the reference, and are the bulk of a real spectrum), lists them by size and
+// hands them to persistent blocks 64 at a time (see "sedp" below).  Its diagnostics need the classes in the
+// reference's order (running sums, and x0 carried from one class to the next): the work kernel leaves x0 per class,
+// sedp_diag_kernel (one block per column) forms x2 in parallel and adds up in order, one thread per sum.
+// Roofline: HBM-side, ff is read once by the scan and the settling classes once more in and out; but a level of a
+// settling profile costs ~200 FP64-pipe instructions per sub-step in a dependent chain (four IEEE divisions, five exact
+// divisions by constants, vterm), so the work kernels are latency / FP64-bound.  No FMA contraction (build.py).
 #include "../../include/mistra_sed.h"
 #include "../../include/mistra_kpp.h"
 
@@ -36,6 +39,12 @@ int mistra_internal_fail(int code, const std::string &msg);  // kpp_api.cu
 namespace {
 
 constexpr int SEDL_T = 64;       // species per block
+#ifndef SEDP_MINB
+#define SEDP_MINB 10              // resident blocks per SM the compiler plans for (register budget)
+#endif
+#ifndef SEDL_MINB
+#define SEDL_MINB 16              // measured (gpurun_out/r02_sed_minb_sweep.txt): more resident warps beat fewer spills
+#endif
 constexpr int SED_MAXN = 512;
 
 __device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }   // gfortran MIN / MAX
@@ -105,19 +114,23 @@ __device__ __forceinline__ double rho_air(double t, double p)
 }
 __device__ __forceinline__ double eta_air(double t) { return 3.7957e-06 + 4.9e-08 * t; }
 
-// SUBROUTINE advsed1 (str.f90:5585-5691) on y[0..nf-1] (stride T in shared memory).  cneg(i) = -c(i+1) of the
-// reference (0-based level i), evaluated once per level from the top down.
-template <int T, class CNEG>
-__device__ __forceinline__ void advsed1_dev(int nf, double *y, CNEG cneg)
+// SUBROUTINE advsed1 (str.f90:5585-5691), one pass over a profile that lives in global memory.  0-based level i:
+// ld(i), 1 <= i <= nf-2, is psi of the level before the pass, st(i, v) takes its new value; psi(1) = x1 (the caller's
+// copy of psi(2), str.f90:2377) and psi(nf) = ytop are registers: ytop is updated, the new psi(1) is returned.
+// cneg(i) = -c(i+1) of the reference, evaluated once per level from the top down.  The five old values of the
+// polynomial fit slide through registers; the values entering the window are loaded four levels at a time, one chunk
+// ahead of their use, so a thread waits for memory once per four levels at most.
+template <class LD, class ST, class CNEG>
+__device__ __forceinline__ double advsed1_pass(int nf, double x1, LD ld, ST st, CNEG cneg, double &ytop)
 {
-#define Y(i) y[(i) * T]
+  auto yv = [&](int j) -> double { return j >= 1 ? ld(j) : (j == 0 ? x1 : 0.0); };
   double cl = cneg(nf - 2);
-  const double yt = Y(nf - 1), ytm = Y(nf - 2);
+  const double yt = ytop, ytm = ld(nf - 2);
   double fm_up = dmin(yt, cl * (yt - (1.0 - cl) * (yt - ytm) * 0.5));          // fm(nf-1)
-  Y(nf - 1) = yt - fm_up;
+  ytop = yt - fm_up;
   double clm = cl;
-  double yp2 = 0.0, yp1 = yt, y0 = ytm, ym1 = Y(nf - 3), ym2 = Y(nf - 4);
-  for (int i = nf - 2; i >= 1; --i) {
+  double yp2 = 0.0, yp1 = yt, y0 = ytm, ym1 = yv(nf - 3), ym2 = yv(nf - 4);
+  auto step = [&](int i, double next) {
     cl = clm;
     clm = cneg(i - 1);
     double a0, a1, a2, a3, a4;
@@ -134,42 +147,61 @@ __device__ __forceinline__ void advsed1_dev(int nf, double *y, CNEG cneg)
       a3 = div_const<3, 8>(yp2 - 2.0 * (yp1 - ym1) - ym2);
       a4 = div_const<15, 8>(yp2 - 4.0 * (yp1 + ym1) + 6.0 * y0 + ym2);
     }
-    const double x1 = 1.0 - 2.0 * cl;
-    const double x2 = x1 * x1;
-    const double x3 = x1 * x2;
+    const double x1_ = 1.0 - 2.0 * cl;
+    const double x2 = x1_ * x1_;
+    const double x3 = x1_ * x2;
     const double ymin = dmin(y0, yp1);
     const double ymax = dmax(y0, yp1);
-    double fmim = dmax(0.0, a0 * cl - a1 * (1.0 - x2) + a2 * (1.0 - x3) - a3 * (1.0 - x1 * x3) + a4 * (1.0 - x2 * x3));
+    double fmim = dmax(0.0, a0 * cl - a1 * (1.0 - x2) + a2 * (1.0 - x3) - a3 * (1.0 - x1_ * x3) + a4 * (1.0 - x2 * x3));
     fmim = dmin(fmim, y0 - ymin + fm_up);
     fmim = dmax(fmim, y0 - ymax + fm_up);
     fmim = dmax(0.0, fmim - (cl - clm) * y0);
     const double w = div_pos(y0, dmax(fmim + 1.e-15, y0));
     const double fm_dn = fmim * w;                                            // fm(i-1)
-    Y(i) = y0 - fm_dn + fm_up;
+    st(i, y0 - fm_dn + fm_up);
     fm_up = fm_dn;
-    yp2 = yp1; yp1 = y0; y0 = ym1; ym1 = ym2;
-    ym2 = (i >= 3) ? Y(i - 3) : 0.0;
+    yp2 = yp1; yp1 = y0; y0 = ym1; ym1 = ym2; ym2 = next;
+  };
+  int i = nf - 2;
+  double n0 = yv(i - 3), n1 = yv(i - 4), n2 = yv(i - 5), n3 = yv(i - 6);
+  while (i >= 1) {
+    const double c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+    n0 = yv(i - 7); n1 = yv(i - 8); n2 = yv(i - 9); n3 = yv(i - 10);          // the chunk after this one
+    step(i, c0);
+    if (i - 1 >= 1) step(i - 1, c1);
+    if (i - 2 >= 1) step(i - 2, c2);
+    if (i - 3 >= 1) step(i - 3, c3);
+    i -= 4;
   }
-  Y(0) = y0 + fm_up;                                                          // y(1) = y(1) + fm(1)
-#undef Y
+  return y0 + fm_up;                                                          // y(1) = y(1) + fm(1)
 }
 
-// SUBROUTINE advsed0 (str.f90:5522-5579): upstream; c(i) = -cneg(i)
-template <int T, class CNEG>
-__device__ __forceinline__ void advsed0_dev(int nf, double *y, CNEG cneg)
+// SUBROUTINE advsed0 (str.f90:5522-5579): upstream, levels 2 .. nf-1 updated in place from the bottom up;
+// c(i) = -cneg(i).  psi(1) and psi(nf) are not changed by it.
+template <class LD, class ST, class CNEG>
+__device__ __forceinline__ void advsed0_pass(int nf, double x1, LD ld, ST st, CNEG cneg, double ytop)
 {
-#define Y(i) y[(i) * T]
-  double ym = Y(0), yc = Y(1);
+  auto yu = [&](int j) -> double { return j <= nf - 2 ? ld(j) : (j == nf - 1 ? ytop : 0.0); };
+  double ym = x1, yc = ld(1);
   const double c0 = -cneg(0);
   double fm_prev = -dmin(0.0, c0) * yc, fp_prev = dmax(0.0, c0) * ym;
-  for (int i = 1; i <= nf - 2; ++i) {
-    const double yn = Y(i + 1);
+  auto step = [&](int i, double yn) {
     const double ci = -cneg(i);
     const double fm_i = -dmin(0.0, ci) * yn, fp_i = dmax(0.0, ci) * yc;
-    Y(i) = yc - fm_prev + fp_prev + fm_i - fp_i;
+    st(i, yc - fm_prev + fp_prev + fm_i - fp_i);
     fm_prev = fm_i; fp_prev = fp_i; ym = yc; yc = yn;
+  };
+  int i = 1;
+  double n0 = yu(i + 1), n1 = yu(i + 2), n2 = yu(i + 3), n3 = yu(i + 4);
+  while (i <= nf - 2) {
+    const double c0_ = n0, c1 = n1, c2 = n2, c3 = n3;
+    n0 = yu(i + 5); n1 = yu(i + 6); n2 = yu(i + 7); n3 = yu(i + 8);
+    step(i, c0_);
+    if (i + 1 <= nf - 2) step(i + 1, c1);
+    if (i + 2 <= nf - 2) step(i + 2, c2);
+    if (i + 3 <= nf - 2) step(i + 3, c3);
+    i += 4;
   }
-#undef Y
 }
 
 // ---- sedp -------------------------------------------------------------------------------------------------------
@@ -257,7 +289,7 @@ sedp_units_kernel(int nc, const int *__restrict__ units, int *__restrict__ unit_
   if (threadIdx.x == 0) unit_off[nc] = s_run;
 }
 
-__global__ void __launch_bounds__(SEDP_W)
+__global__ void __launch_bounds__(SEDP_W, SEDP_MINB)
 sedp_work_kernel(mistra_sedp_args a, int nc, const int *__restrict__ unit_off, const unsigned short *__restrict__ list,
                  const int *__restrict__ cnt, double *__restrict__ x0c, int *__restrict__ counter)
 {
@@ -265,7 +297,7 @@ sedp_work_kernel(mistra_sedp_args a, int nc, const int *__restrict__ unit_off, c
   __shared__ int s_u;
   const int n = a.n, nf = a.nf, row = a.nka * a.nkt;
   double *s_detw = sm, *s_deta = sm + nf, *s_t = sm + 2 * nf, *s_p = sm + 3 * nf, *s_rho = sm + 4 * nf,
-         *s_eta = sm + 5 * nf, *psi = sm + 6 * nf + threadIdx.x;
+         *s_eta = sm + 5 * nf;
   const int total = unit_off[nc];
   for (;;) {
     __syncthreads();                                                          // the unit before is done with the tables
@@ -290,31 +322,41 @@ sedp_work_kernel(mistra_sedp_args a, int nc, const int *__restrict__ unit_off, c
     const int q = list[col * row + i];
     double *f = a.ff + col * (size_t)n * row + q;
     const double rqq = a.rq[q], aq = rqq * 1.e-6;
-#pragma unroll 11
-    for (int k = 1; k < nf; ++k) psi[k * SEDP_W] = f[(size_t)k * row] * s_detw[k];
     const double ww = -1. * vterm_lev(aq, s_t[nf - 1], s_p[nf - 1], s_rho[nf - 1], s_eta[nf - 1]);
     const double x3 = -s_deta[1], vdq = a.vd[col * row + q];
-    double dt0 = a.dt, x0 = 0.0;
+    double ytop = f[(size_t)(nf - 1) * row] * s_detw[nf - 1];                 // psi(nf)
+    double dt0 = a.dt, x0 = 0.0, last = 0.0;
+    bool first = true, finished = false;                                      // array holds ff (first) or psi; ff written
     for (int it = 0; dt0 > 0.1 && it < MISTRA_SED_MAXSUB; ++it) {             // str.f90:2355-2385
       const double dtmax = dmin(dt0, x3 / (ww));
       double c2 = dtmax / s_deta[1] * (-1. * vterm_lev(aq, s_t[1], s_p[1], s_rho[1], s_eta[1]));
       c2 = dmin(c2, dtmax / s_deta[1] * vdq * (-1.));
       dt0 = dt0 - dtmax;
-      const double x1 = psi[1 * SEDP_W];
-      psi[0] = x1;
+      const bool fin = !(dt0 > 0.1);                                          // the last pass writes ff = psi / detw (2388-2391)
       auto cneg = [&](int lev) -> double {
         if (lev <= 1) return -c2;
         return -(dtmax / s_deta[lev] * (-1. * vterm_lev(aq, s_t[lev], s_p[lev], s_rho[lev], s_eta[lev])));
       };
-      if (rqq < 1.0) advsed0_dev<SEDP_W>(nf, psi, cneg); else advsed1_dev<SEDP_W>(nf, psi, cneg);
-      x0 = x0 + psi[0] - x1;
+      auto ld = [&](int i) -> double { const double v = f[(size_t)i * row]; return first ? v * s_detw[i] : v; };
+      auto st = [&](int i, double v) {
+        if (fin) { v = div_pos(v, s_detw[i]); if (i == nf - 2) last = v; }
+        f[(size_t)i * row] = v;
+      };
+      const double x1 = ld(1);
+      double p1 = x1;
+      if (rqq < 1.0) advsed0_pass(nf, x1, ld, st, cneg, ytop); else p1 = advsed1_pass(nf, x1, ld, st, cneg, ytop);
+      x0 = x0 + p1 - x1;
+      first = false;
+      finished = fin;
     }
-    double last = 0.0;
-    for (int k = 1; k < nf - 1; ++k) {                                        // 2388-2391
-      last = div_pos(psi[k * SEDP_W], s_detw[k]);
-      f[(size_t)k * row] = last;
-    }
-    f[(size_t)(nf - 1) * row] = last;
+    if (!finished)                                                            // no pass at all (dt <= 0.1) or the pass limit
+      for (int k = 1; k < nf - 1; ++k) {
+        double v = f[(size_t)k * row];
+        if (first) v = v * s_detw[k];
+        last = div_pos(v, s_detw[k]);
+        f[(size_t)k * row] = last;
+      }
+    f[(size_t)(nf - 1) * row] = last;                                         // ff(jt,ia,nf) = ff(jt,ia,nf-1)
     x0c[col * row + q] = x0;
   }
 }
@@ -369,12 +411,12 @@ sedp_diag_kernel(mistra_sedp_args a, const double *__restrict__ x0c, const unsig
 }
 
 // ---- sedl -------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SEDL_T)
+__global__ void __launch_bounds__(SEDL_T, SEDL_MINB)
 sedl_kernel(mistra_sedl_args a, double *__restrict__ s, int jx, int nchunk)
 {
   extern __shared__ double sm[];
   const int n = a.n, nf = a.nf, nkc = a.nkc;
-  double *s_detw = sm, *s_cc = sm + nf, *psi = sm + 2 * nf + threadIdx.x;
+  double *s_detw = sm, *s_cc = sm + nf;
   const size_t col = blockIdx.y;
   const int kc = blockIdx.x / nchunk, l = (blockIdx.x % nchunk) * SEDL_T + threadIdx.x;
   for (int k = threadIdx.x; k < nf; k += SEDL_T) {                            // str.f90:2691-2701
@@ -393,19 +435,28 @@ sedl_kernel(mistra_sedl_args a, double *__restrict__ s, int jx, int nchunk)
   if (l >= jx) return;
   const size_t row = (size_t)nkc * jx;
   double *sl = s + col * (size_t)n * row + (size_t)kc * jx + l;
-#pragma unroll 8
-  for (int k = 1; k < nf; ++k) psi[k * SEDL_T] = sl[(size_t)k * row] * s_detw[k];
+  double ytop = sl[(size_t)(nf - 1) * row] * s_detw[nf - 1];                  // psi(nf): advected, never written back
   double dt0 = a.dt, x0 = 0.0;
   const double xxxt = -.999 / s_cc[1];
+  bool first = true, finished = false;
   for (int it = 0; dt0 > 0.1 && it < MISTRA_SED_MAXSUB; ++it) {               // 2708-2720
     const double dtmax = dmin(dt0, xxxt);
     dt0 = dt0 - dtmax;
-    const double x1 = psi[1 * SEDL_T];
-    psi[0] = x1;
-    advsed1_dev<SEDL_T>(nf, psi, [&](int i) -> double { return -(s_cc[i < 1 ? 1 : i] * dtmax); });
-    x0 = x0 + psi[0] - x1;
+    const bool fin = !(dt0 > 0.1);                                            // the last pass writes sl1 = psi / detw (2723-2725)
+    auto ld = [&](int i) -> double { const double v = sl[(size_t)i * row]; return first ? v * s_detw[i] : v; };
+    auto st = [&](int i, double v) { sl[(size_t)i * row] = fin ? div_pos(v, s_detw[i]) : v; };
+    const double x1 = ld(1);
+    const double p1 = advsed1_pass(nf, x1, ld, st, [&](int i) -> double { return -(s_cc[i < 1 ? 1 : i] * dtmax); }, ytop);
+    x0 = x0 + p1 - x1;
+    first = false;
+    finished = fin;
   }
-  for (int k = 1; k < nf - 1; ++k) sl[(size_t)k * row] = div_pos(psi[k * SEDL_T], s_detw[k]);
+  if (!finished)
+    for (int k = 1; k < nf - 1; ++k) {
+      double v = sl[(size_t)k * row];
+      if (first) v = v * s_detw[k];
+      sl[(size_t)k * row] = div_pos(v, s_detw[k]);
+    }
   sl[0] = sl[0] + x0 * a.deta[1];                                             // wet deposition, 2727
 }
 
@@ -555,7 +606,7 @@ int mistra_sedp_device(int64_t ncol, const mistra_sedp_args *d_a, void *stream)
   unsigned char *flag = (unsigned char *)(wb + o_flag);
   unsigned short *list = (unsigned short *)(wb + o_list);
   int *cnt = (int *)(wb + o_cnt), *units = (int *)(wb + o_units), *unit_off = (int *)(wb + o_off), *counter = (int *)(wb + o_ctr);
-  const size_t smem = ((size_t)6 * a.nf + (size_t)a.nf * SEDP_W) * sizeof(double);
+  const size_t smem = (size_t)6 * a.nf * sizeof(double);
   static int nsm[16] = {};
   if (!nsm[dev]) CKW(cudaDeviceGetAttribute(&nsm[dev], cudaDevAttrMultiProcessorCount, dev));
   int per_sm = 1;
@@ -613,7 +664,7 @@ int mistra_sedl_device(int64_t ncol, const mistra_sedl_args *d_a, void *stream)
   int dev = -1;
   if (int rc = current_device(&dev)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = ((size_t)2 * a.nf + (size_t)a.nf * SEDL_T) * sizeof(double);
+  const size_t smem = (size_t)2 * a.nf * sizeof(double);
   const size_t chunk = 32768;
   for (size_t c0 = 0; c0 < (size_t)ncol; c0 += chunk) {
     const size_t nc = std::min(chunk, (size_t)ncol - c0);
