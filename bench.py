@@ -474,6 +474,9 @@ def run_b200(args):
         t_end.record(stream)
         barrier()
     launches = kpp.launch_count() - l0
+    handed = torch.tensor([float(kpp.handoff_count())], dtype=torch.float64, device=dev)   # last call = the last mechanism
+    if world > 1:
+        dist.all_reduce(handed)
     ms_total = t_start.elapsed_time(t_end)
     tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -669,6 +672,10 @@ def run_b200(args):
                        "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no explicit flush"
                              % (sum(d["rc"].numel() * 8 + d["var"].numel() * 8 for d in dbatches) * 1e-9)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "handoff": {"cells_continued_on_chip_last_call": int(handed.item()),
+                        "note": "mistra_kpp_set_handoff default: an aer cell that has made 12 step attempts in the cell-per-thread "
+                                "kernel is continued by the on-chip kernel (one extra launch per call, counted in gpu_launches); "
+                                "value / roofline time the whole call, hand-off pass included; MISTRA_KPP_HANDOFF=0 switches it off"},
             "roofline": roof, "cpu_baseline": cpu, "parity": parity,
             "tot": extras.get("tot") if extras else None,
             "cold_start": extras.get("cold_start") if extras else None,

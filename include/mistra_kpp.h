@@ -148,6 +148,22 @@ int mistra_kpp_get_kernel(int mech);
 int mistra_kpp_kernel_for(int mech, int64_t ncell);
 int64_t mistra_kpp_launch_count_variant(int variant);
 
+/* Hand-off of long cells between the two variants.  In the cell-per-thread kernel every Ros3 step of a cell takes
+ * milliseconds (tens of thousands of cells share the device), so a cell that needs many steps - rejected steps at a
+ * day / night or cloud edge, a transient - keeps its lane long after the rest of the batch has finished and the launch
+ * waits for it.  With steps > 0 a cell that has made `steps` step attempts without reaching TOUT is retired at that step
+ * boundary and continued, from its (T, H, counters) and VAR, by the on-chip kernel, which runs a step 40 times faster:
+ * the same sequence of steps as without the hand-off (the two kernels differ by rounding only, within the parity
+ * contract; bit-identical in the strict build).  Which cells are handed over depends on their own step count only, so
+ * results do not depend on timing.  steps = -1 (default): 12 for aer when the library chose the kernel by the batch
+ * size, off when a variant is pinned, and for gas / tot; 0 = off.  MISTRA_KPP_HANDOFF=<steps> in the environment sets
+ * it for aer.  Applies to mistra_kpp_integrate_device (the hand-off pass runs once, after the last chunk of the call);
+ * the host-buffer entries recycle their device staging per chunk and do not hand cells over.  Returns 0 or a
+ * negative MISTRA_KPP_E* code. */
+int mistra_kpp_set_handoff(int mech, int steps);
+/* Cells the last mistra_kpp_integrate_device call on the current device handed over (synchronises with the device). */
+int64_t mistra_kpp_handoff_count(void);
+
 /* Release what the KPP integrators hold on every device they ran on: lane workspaces, on-chip instruction tables,
  * staging buffers, streams and events.  (The grid caches and scratch buffers of the particle-grid and column
  * operators - mistra_bins.h, mistra_kon.h, ... - are small and live until the process exits.) */

@@ -46,7 +46,9 @@ struct DeviceState {
   int dev = -1;
   int num_sm = 0;
   cudaStream_t stream = nullptr;
-  unsigned long long *counter = nullptr;   // [2]: one cell counter per pipeline slot
+  unsigned long long *counter = nullptr;   // [3]: one cell counter per pipeline slot, [2]: the hand-off pass
+  char *handoff = nullptr;                 // mistra_kpp_integrate_device: deferred-cell count and list, (T, H) per cell, spare statistics
+  size_t handoff_bytes = 0;
   MechState mech[3];
   // device staging for the host-buffer entry
   void *d_stage = nullptr;
@@ -121,7 +123,7 @@ int get_device(DeviceState **out)
     d.dev = dev;
     d.num_sm = p.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-    CK(cudaMalloc(&d.counter, 2 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&d.counter, 3 * sizeof(unsigned long long)));
     for (auto &e : d.ev_slot) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     d.init = true;
   }
@@ -194,6 +196,19 @@ bool want_onchip(const KppMechInfo *mi, int mech, int64_t ncell)
   if (v >= 0) return v == 1;
   return ncell <= kOnchipMaxCells[mech];
 }
+// Hand-off of long cells (kpp_batch.h): step attempts a cell may make in the cell-per-thread kernel before the on-chip
+// kernel continues it.  -1 = default: 12 for aer when the library chose the kernel by batch size (a steady-state cell
+// needs 7 - 8 attempts; a cell with rejected steps or in a transient needs tens to hundreds and would hold a lane at
+// 6.5 ms per step, the on-chip kernel runs it at 0.15 ms per step), 0 otherwise and for gas / tot.
+int g_handoff[3] = {-1, -1, -1};
+int handoff_steps(const KppMechInfo *mi, int mech)
+{
+  if (!mi->oc) return 0;
+  if (g_handoff[mech] >= 0) return g_handoff[mech];
+  if (const char *e = getenv("MISTRA_KPP_HANDOFF")) return mech == 1 && atoi(e) > 0 ? atoi(e) : 0;
+  if (g_variant[mech] >= 0 || getenv("MISTRA_KPP_ONCHIP")) return 0;
+  return mech == 1 ? 12 : 0;
+}
 int ensure_mech(DeviceState &d, int mech, const KppMechInfo *mi, int f32, cudaStream_t st, bool onchip)
 {
   MechState &ms = d.mech[mech];
@@ -251,10 +266,38 @@ int ensure_mech(DeviceState &d, int mech, const KppMechInfo *mi, int f32, cudaSt
   return 0;
 }
 
+// Hand-off context of one mistra_kpp_integrate_device call (kpp_batch.h): arrays over the cells of the whole call.
+struct Handoff {
+  int soft;
+  unsigned long long *count;
+  long long *list;
+  double *cont;
+  int32_t *stats;      // used when the caller keeps no statistics
+};
+
+int handoff_begin(DeviceState &d, int64_t ncell, int soft, Handoff *ho, cudaStream_t st)
+{
+  // [count | list: ncell x 8 | cont: ncell x 16 | statistics: ncell x 32]
+  const size_t o_list = 256, o_cont = o_list + (((size_t)ncell * 8 + 255) & ~(size_t)255),
+               o_stats = o_cont + (((size_t)ncell * 16 + 255) & ~(size_t)255), need = o_stats + (size_t)ncell * 32;
+  if (d.handoff_bytes < need) {
+    if (d.handoff) { CK(cudaDeviceSynchronize()); cudaFree(d.handoff); d.handoff = nullptr; d.handoff_bytes = 0; }
+    CK(cudaMalloc(&d.handoff, need));
+    d.handoff_bytes = need;
+  }
+  ho->soft = soft;
+  ho->count = (unsigned long long *)d.handoff;
+  ho->list = (long long *)(d.handoff + o_list);
+  ho->cont = (double *)(d.handoff + o_cont);
+  ho->stats = (int32_t *)(d.handoff + o_stats);
+  CK(cudaMemsetAsync(ho->count, 0, sizeof(unsigned long long), st));
+  return 0;
+}
+
 int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rconst,
                   const double *d_fix, double *d_var, double t0, double t1,
                   const mistra_kpp_opts *o, int32_t *d_ierr, int32_t *d_stats, double *d_hexit,
-                  double *d_texit, cudaStream_t st, int slot, bool onchip)
+                  double *d_texit, cudaStream_t st, int slot, bool onchip, const Handoff *ho = nullptr, int64_t off = 0)
 {
   const KppMechInfo *mi = mech_info(mech);
   KppBatch b;
@@ -286,6 +329,14 @@ int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rcons
   b.counter = d.counter + slot;
   CK(cudaStreamWaitEvent(st, d.ev_slot[slot], 0));
   CK(cudaMemsetAsync(b.counter, 0, sizeof(unsigned long long), st));
+  if (ho && !onchip) {                                 // long cells are retired at a step boundary (kpp_batch.h)
+    b.soft_steps = ho->soft;
+    b.defer_count = ho->count;
+    b.defer_list = ho->list;
+    b.cell_base = off;
+    b.cont = ho->cont + 2 * off;
+    if (!b.stats) b.stats = ho->stats + 8 * off;
+  }
   if (onchip) {
     const long long need = (ncell + mi->oc->slots - 1) / mi->oc->slots;
     int blocks = (int)(need < ms.oc_blocks ? need : ms.oc_blocks);
@@ -301,6 +352,36 @@ int launch_device(DeviceState &d, int mech, int64_t ncell, const double *d_rcons
   return 0;
 }
 
+
+// The cells the cell-per-thread launches of a call have retired unfinished, continued by the on-chip kernel: one
+// launch at the end of the call (the on-chip blocks need whole SMs, which the chunks of pass 1 only free at their end).
+int launch_handoff_pass(DeviceState &d, int mech, int64_t ncell, const double *d_rconst, const double *d_fix, double *d_var,
+                        double t0, double t1, const mistra_kpp_opts *o, int32_t *d_ierr, int32_t *d_stats, double *d_hexit,
+                        double *d_texit, cudaStream_t st, const Handoff &ho)
+{
+  const KppMechInfo *mi = mech_info(mech);
+  KppBatch b;
+  memset(&b, 0, sizeof(b));
+  int rc = decode_opts(o, t0, t1, &b);
+  if (rc) return rc;
+  MechState &ms = d.mech[mech];
+  b.rconst = d_rconst; b.fix = d_fix; b.var = d_var;
+  b.ierr = d_ierr; b.stats = d_stats ? d_stats : ho.stats; b.hexit = d_hexit; b.texit = d_texit;
+  b.ncell = ncell;
+  b.ws = ms.oc_ws;
+  b.oc_tab = ms.oc_tab; b.oc_aux = g_oc_aux; b.oc_flags = g_oc_flags;
+  b.resume = 1;
+  b.cont = ho.cont;
+  b.list = ho.list;
+  b.list_count = ho.count;
+  b.counter = d.counter + 2;
+  CK(cudaMemsetAsync(b.counter, 0, sizeof(unsigned long long), st));
+  const long long need = (ncell + mi->oc->slots - 1) / mi->oc->slots;
+  CK(mi->oc->launch(b, (int)(need < ms.oc_blocks ? need : ms.oc_blocks), st));
+  g_launches.fetch_add(1);
+  g_launches_variant[1].fetch_add(1);
+  return 0;
+}
 
 // ---- compact rate inputs -> the NSPEC-indexed arrays Update_RCONST_x reads (include/mistra_kpp_rates.h) ------------
 __global__ void rates_expand_kernel(double *__restrict__ full, const double *__restrict__ val, const int *__restrict__ idx,
@@ -434,6 +515,12 @@ int mistra_kpp_integrate_device(int mech, int64_t ncell, const double *d_rconst,
   // +3 %, sixteen chunks more; measured).  MISTRA_KPP_SPLIT=0 switches it off.
   static const bool split = !(getenv("MISTRA_KPP_SPLIT") && atoi(getenv("MISTRA_KPP_SPLIT")) == 0);
   const bool oc = want_onchip(mech_info(mech), mech, ncell);
+  Handoff ho, *hop = nullptr;
+  if (!oc && ncell > 0 && handoff_steps(mech_info(mech), mech) > 0) {
+    if ((rc = ensure_mech(*d, mech, mech_info(mech), o ? (o->f32_literals ? 1 : 0) : 1, st, true))) return rc;
+    if ((rc = handoff_begin(*d, ncell, handoff_steps(mech_info(mech), mech), &ho, st))) return rc;
+    hop = &ho;
+  }
   if (split && !oc && ncell >= 8LL * d->num_sm * 2 * KPP_BLOCK) {
     const KppMechInfo *mi = mech_info(mech);
     if ((rc = ensure_streams(d))) return rc;
@@ -451,15 +538,19 @@ int mistra_kpp_integrate_device(int mech, int64_t ncell, const double *d_rconst,
       if ((rc = launch_device(*d, mech, m, d_rconst + off * mi->nreact, d_fix + off * mi->nfix, d_var + off * mi->nvar,
                               t0, t1, o, d_ierr ? d_ierr + off : nullptr, d_stats ? d_stats + 8 * off : nullptr,
                               d_hexit ? d_hexit + off : nullptr, d_texit ? d_texit + off : nullptr,
-                              slot ? d->s_k2 : st, slot, false)))
+                              slot ? d->s_k2 : st, slot, false, hop, off)))
         return rc;
     }
     CK(cudaEventRecord(d->ev_join, d->s_k2));
     CK(cudaStreamWaitEvent(st, d->ev_join, 0));
+    if (hop) return launch_handoff_pass(*d, mech, ncell, d_rconst, d_fix, d_var, t0, t1, o, d_ierr, d_stats, d_hexit, d_texit, st, ho);
     return 0;
   }
-  return launch_device(*d, mech, ncell, d_rconst, d_fix, d_var, t0, t1, o, d_ierr, d_stats,
-                       d_hexit, d_texit, st, 0, oc);
+  if ((rc = launch_device(*d, mech, ncell, d_rconst, d_fix, d_var, t0, t1, o, d_ierr, d_stats,
+                          d_hexit, d_texit, st, 0, oc, hop, 0)))
+    return rc;
+  if (hop) return launch_handoff_pass(*d, mech, ncell, d_rconst, d_fix, d_var, t0, t1, o, d_ierr, d_stats, d_hexit, d_texit, st, ho);
+  return 0;
 }
 
 int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const double *fix,
@@ -878,6 +969,30 @@ int mistra_kpp_set_kernel(int mech, int variant)
   return 0;
 }
 
+int mistra_kpp_set_handoff(int mech, int steps)
+{
+  if (!mech_info(mech)) return fail(MISTRA_KPP_EINVAL, "unknown mechanism id");
+  if (steps < -1) return fail(MISTRA_KPP_EINVAL, "steps: -1 default, 0 off, > 0 step attempts before the hand-off");
+  if (steps > 0 && !mech_info(mech)->oc) return fail(MISTRA_KPP_EINVAL, "this mechanism has no on-chip kernel to hand over to");
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_handoff[mech] = steps;
+  return 0;
+}
+
+int64_t mistra_kpp_handoff_count(void)
+{
+  DeviceState *d;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (get_device(&d)) return -1;
+  }
+  std::lock_guard<std::mutex> dl(g_dev_mu[d->dev]);
+  if (!d->handoff) return 0;
+  unsigned long long h = 0;
+  if (cudaMemcpy(&h, d->handoff, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)h;
+}
+
 int mistra_kpp_get_kernel(int mech)
 {
   if (mech < 0 || mech > 2) return fail(MISTRA_KPP_EINVAL, "mech must be 0, 1 or 2");
@@ -923,6 +1038,8 @@ int mistra_kpp_finalize(void)
       m = MechState();
     }
     if (d.counter) cudaFree(d.counter);
+    if (d.handoff) cudaFree(d.handoff);
+    d.handoff = nullptr; d.handoff_bytes = 0;
     for (auto &e : d.ev_slot) if (e) cudaEventDestroy(e);
     if (d.d_stage) cudaFree(d.d_stage);
     if (d.d_rates) cudaFree(d.d_rates);

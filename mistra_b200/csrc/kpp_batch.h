@@ -29,7 +29,20 @@ struct KppBatch {
   // decoded options (Rosenbrock_x, gas.f:950-1051)
   double t0, t1, rtol, atol, hmin, hmax, hstart, facmin, facmax, facrej, facsafe;
   int max_steps, autonomous;
+  // hand-off of long cells (kpp_api.cu: launch_device).  Pass 1 (cell per thread): a cell that has made soft_steps
+  // step attempts and is not finished is retired at the step boundary with ierr = KPP_IERR_DEFERRED - VAR, the
+  // counters (stats) and (T, H) in cont[cell][2] written out, its index appended to defer_list.  Pass 2 (on-chip
+  // kernel, resume = 1) takes the cells list[0 .. *list_count) and continues each from cont / stats: the same
+  // sequence of steps as without the hand-off, so a straggler no longer occupies a lane of the slow-per-step kernel.
+  int soft_steps, resume;
+  long long cell_base;           // index of this launch's first cell in the arrays of the whole call (defer_list holds those)
+  long long *defer_list;
+  unsigned long long *defer_count;
+  double *cont;
+  const long long *list;
+  const unsigned long long *list_count;
 };
+#define KPP_IERR_DEFERRED 2
 
 struct KppOnchipInfo;   // csrc/kpp_onchip.h
 

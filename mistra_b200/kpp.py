@@ -368,6 +368,20 @@ def set_kernel(mech, variant, strict=False):
     _check(L, L.mistra_kpp_set_kernel(mech, variant))
 
 
+def set_handoff(mech, steps, strict=False):
+    """Step attempts a cell may make in the cell-per-thread kernel before the on-chip kernel continues it
+    (include/mistra_kpp.h): -1 = default (12 for aer when the kernel is chosen by batch size), 0 = off."""
+    L = library(strict)
+    _check(L, L.mistra_kpp_set_handoff(mech, steps))
+
+
+def handoff_count(strict=False):
+    """Cells the last integrate_device call on the current device handed over to the on-chip kernel."""
+    L = library(strict)
+    L.mistra_kpp_handoff_count.restype = C.c_int64
+    return int(L.mistra_kpp_handoff_count())
+
+
 def get_kernel(mech, strict=False):
     """Pinned variant of a mechanism, -1 = chosen per call by the batch size."""
     return int(library(strict).mistra_kpp_get_kernel(mech))

@@ -139,3 +139,96 @@ def test_same_results_as_the_default_kernel(kpp, cuda_device):
     assert np.array_equal(ierr_a, ierr_b)
     assert (st_a[:, 2:5] == st_b[:, 2:5]).all(axis=1).mean() >= 0.99
     assert util.rel_err(a, b).max() <= 1e-5
+
+
+def run_dev(kpp, cuda_device, rc, fix, var, strict=False, diag=True):
+    """mistra_kpp_integrate_device on copies of the host arrays; returns numpy (var, ierr, stats, hexit, texit)."""
+    import torch
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    n = var.shape[0]
+    vd = t(var)
+    ie = torch.zeros(n, dtype=torch.int32, device=cuda_device) if diag else None
+    sd = torch.zeros((n, 8), dtype=torch.int32, device=cuda_device) if diag else None
+    hx = torch.zeros(n, dtype=torch.float64, device=cuda_device) if diag else None
+    tx = torch.zeros(n, dtype=torch.float64, device=cuda_device) if diag else None
+    kpp.integrate_device(1, t(rc), t(fix), vd, ierr=ie, stats=sd, hexit=hx, texit=tx, strict=strict)
+    torch.cuda.synchronize()
+    c = lambda x: None if x is None else x.cpu().numpy()
+    return c(vd), c(ie), c(sd), c(hx), c(tx)
+
+
+def test_handoff_of_long_cells(kpp, cuda_device, oracle):
+    """mistra_kpp_set_handoff (device entry): cells that exceed the step budget in the cell-per-thread kernel are
+    continued by the on-chip kernel from (T, H, counters).  Cold aer cells (~180 steps each): every cell is handed over
+    after 12 attempts; the step history is that of an uninterrupted integration - identical in the strict build, within
+    rounding in the product build - and cells that finish within the budget are not touched by the second pass."""
+    ens = synthetic.AerEnsemble(2)
+    rc = ens.rconst(ens.var)
+    ref, ierr_o, stats_o, hexit_o, _ = oracle.integrate(1, rc, ens.fix, ens.var, nthreads=8)
+    run = lambda *a, **k: run_dev(kpp, cuda_device, *a, **k)
+    try:
+        for strict in (False, True):
+            kpp.set_kernel(1, 0, strict=strict)
+            kpp.set_handoff(1, 0, strict=strict)
+        plain, ierr_p, stats_p, hexit_p, texit_p = run(rc, ens.fix, ens.var)
+        n0, n1 = kpp.launch_count_variant(0), kpp.launch_count_variant(1)
+        kpp.set_handoff(1, 12)
+        out, ierr, stats, hexit, texit = run(rc, ens.fix, ens.var)
+        assert kpp.launch_count_variant(0) == n0 + 1 and kpp.launch_count_variant(1) == n1 + 1
+        assert (stats_p[:, 2] > 12).all()                            # every cell exceeded the budget ...
+        assert np.array_equal(ierr, ierr_p) and (ierr == 1).all() and np.array_equal(texit, texit_p)
+        same = (stats == stats_p).all(axis=1)
+        assert same.mean() >= 0.95                                   # ... and went on as if nothing had happened
+        assert util.rel_err(out[same], plain[same]).max() <= 1e-5
+        compare(out, ref, stats, stats_o, ierr, ierr_o, hexit, hexit_o, locked_tol=1e-5, hexit_rtol=1e-4)
+        # strict build: both kernels reproduce the reference order, so the hand-off must be invisible
+        kpp.set_handoff(1, 12, strict=True)
+        outs, ierrs, statss, hexits, _ = run(rc, ens.fix, ens.var, strict=True)
+        kpp.set_handoff(1, 0, strict=True)
+        outp, ierrp, statsp, hexitp, _ = run(rc, ens.fix, ens.var, strict=True)
+        assert np.array_equal(statss, stats_o) and np.array_equal(ierrs, ierr_o) and np.array_equal(statss, statsp)
+        assert np.array_equal(hexits, hexitp) and util.rel_err(outs, outp).max() <= 1e-12
+        # budgets around the step counts of a spun-up ensemble: nobody / some / everybody handed over
+        var = ref
+        for _ in range(2):
+            var = kpp.integrate(1, ens.rconst(var), ens.fix, var)[0]
+        rc2 = ens.rconst(var)
+        base, ierr_b, stats_b, _, _ = run(rc2, ens.fix, var)
+        for budget in (64, int(np.median(stats_b[:, 2])), 2):
+            kpp.set_handoff(1, budget)
+            o2, ierr2, stats2, _, _ = run(rc2, ens.fix, var)
+            kpp.set_handoff(1, 0)
+            assert np.array_equal(ierr2, ierr_b)
+            moved = stats_b[:, 2] > budget                           # finished within the budget: never handed over
+            assert np.array_equal(o2[~moved], base[~moved]) and np.array_equal(stats2[~moved], stats_b[~moved])
+            assert util.rel_err(o2, base).max() <= 1e-5
+        kpp.set_handoff(1, 3)
+        o3 = run(rc2, ens.fix, var, diag=False)[0]                   # the caller keeps no ierr / stats / hexit arrays
+        assert util.rel_err(o3, base).max() <= 1e-5
+        # failing cells are handed over like any other and fail the same way
+        bad = var.copy()
+        bad[5, 10] = np.nan
+        kpp.set_handoff(1, 0)
+        ierr_x = run(rc2, ens.fix, bad)[1]
+        kpp.set_handoff(1, 4)
+        ierr_y = run(rc2, ens.fix, bad)[1]
+        assert np.array_equal(ierr_x, ierr_y) and ierr_y[5] < 0
+        # a long batch (chunks on two streams, one hand-off pass at the end) with a few cold cells among spun-up ones
+        reps = 1600                                                  # 313 600 cells: above the chunking threshold
+        big_var, big_fix, big_rc = np.tile(var, (reps, 1)), np.tile(ens.fix, (reps, 1)), np.tile(rc2, (reps, 1))
+        cold = np.arange(7, big_var.shape[0], 9973)
+        big_var[cold], big_rc[cold] = ens.var[cold % ens.ncell], rc[cold % ens.ncell]
+        kpp.set_handoff(1, 0)
+        b0, ierr0, st0, _, _ = run(big_rc, big_fix, big_var)
+        kpp.set_handoff(1, 12)
+        b1, ierr1, st1, _, _ = run(big_rc, big_fix, big_var)
+        assert np.array_equal(ierr0, ierr1) and (st0[cold, 2] > 12).all()
+        quick = st0[:, 2] <= 12
+        assert quick.mean() > 0.99 and np.array_equal(b1[quick], b0[quick]) and np.array_equal(st1[quick], st0[quick])
+        assert (st1[~quick] == st0[~quick]).all(axis=1).mean() >= 0.9 and util.rel_err(b1, b0).max() <= 1e-5
+        with pytest.raises(kpp.KppError):
+            kpp.set_handoff(2, 5)                                    # tot has no on-chip kernel
+    finally:
+        for strict in (False, True):
+            kpp.set_handoff(1, -1, strict=strict)
+            kpp.set_kernel(1, 0, strict=strict)
