@@ -290,6 +290,7 @@ int handoff_begin(DeviceState &d, int64_t ncell, int soft, Handoff *ho, cudaStre
   ho->list = (long long *)(d.handoff + o_list);
   ho->cont = (double *)(d.handoff + o_cont);
   ho->stats = (int32_t *)(d.handoff + o_stats);
+  CK(cudaStreamWaitEvent(st, d.ev_slot[0], 0));         // the hand-off pass of a call on another stream may still read them
   CK(cudaMemsetAsync(ho->count, 0, sizeof(unsigned long long), st));
   return 0;
 }
@@ -378,6 +379,7 @@ int launch_handoff_pass(DeviceState &d, int mech, int64_t ncell, const double *d
   CK(cudaMemsetAsync(b.counter, 0, sizeof(unsigned long long), st));
   const long long need = (ncell + mi->oc->slots - 1) / mi->oc->slots;
   CK(mi->oc->launch(b, (int)(need < ms.oc_blocks ? need : ms.oc_blocks), st));
+  CK(cudaEventRecord(d.ev_slot[0], st));
   g_launches.fetch_add(1);
   g_launches_variant[1].fetch_add(1);
   return 0;

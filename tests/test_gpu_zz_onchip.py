@@ -201,10 +201,11 @@ def test_handoff_of_long_cells(kpp, cuda_device, oracle):
             assert np.array_equal(ierr2, ierr_b)
             moved = stats_b[:, 2] > budget                           # finished within the budget: never handed over
             assert np.array_equal(o2[~moved], base[~moved]) and np.array_equal(stats2[~moved], stats_b[~moved])
-            assert util.rel_err(o2, base).max() <= 1e-5
+            assert util.rel_err(o2, base).max() <= 1e-4             # three steps after a cold start: rounding differences
+                                                                     # between the kernels are still amplified (RTOL = 1e-3)
         kpp.set_handoff(1, 3)
         o3 = run(rc2, ens.fix, var, diag=False)[0]                   # the caller keeps no ierr / stats / hexit arrays
-        assert util.rel_err(o3, base).max() <= 1e-5
+        assert util.rel_err(o3, base).max() <= 1e-4
         # failing cells are handed over like any other and fail the same way
         bad = var.copy()
         bad[5, 10] = np.nan
@@ -225,7 +226,7 @@ def test_handoff_of_long_cells(kpp, cuda_device, oracle):
         assert np.array_equal(ierr0, ierr1) and (st0[cold, 2] > 12).all()
         quick = st0[:, 2] <= 12
         assert quick.mean() > 0.99 and np.array_equal(b1[quick], b0[quick]) and np.array_equal(st1[quick], st0[quick])
-        assert (st1[~quick] == st0[~quick]).all(axis=1).mean() >= 0.9 and util.rel_err(b1, b0).max() <= 1e-5
+        assert (st1[~quick] == st0[~quick]).all(axis=1).mean() >= 0.9 and util.rel_err(b1, b0).max() <= 1e-4
         with pytest.raises(kpp.KppError):
             kpp.set_handoff(2, 5)                                    # tot has no on-chip kernel
     finally:
