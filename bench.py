@@ -1113,6 +1113,46 @@ def run_next_rows_leg(args, dev, world, rank, barrier):
         res["sedl"]["cpu_baseline"] = {"value": m * reps / dt, "unit": "columns/s", "cores": os.cpu_count(), "kind": "port",
                                        "sample": "%d x %d columns, OpenMP over columns, %.1f s" % (reps, m, dt)}
     del sv, sk, sd
+    # ---- the layer loop of kpp_driver (row a15): per-layer scalars, switches and the layers sorted by mechanism ----
+    from mistra_b200 import driver as drv
+    from oracle import driver_oracle as dvo
+    ncd_, nfd = max(1, args.cols // 5), 100                         # 2000 columns x 150 levels = 300 000 layers
+    dcol = drv.synthetic_columns(ncd_, nlev, nfd, 4, 93, 24, 20261018 + rank)
+    dcol["u0"] = np.random.default_rng(20261018 + rank).uniform(-0.2, 1.0, ncd_)
+    cfg = dict(nf=nfd, halo=True, iod=True, lpBuys13_0D=False, neula=0, box=False, n_bl=2, kinv=70, dt_ch=10.0)
+    adv_row, xadv = np.array([4, -1, 17, 60], dtype=np.int32), np.array([1e-9, 2e-9, -3e-10, 1e-8])
+    dvd = {k: t(v) for k, v in dcol.items() if k != "cloud"}
+    dvd["cloud"] = torch.from_numpy(dcol["cloud"].astype(np.int32)).to(dev)
+    nl = ncd_ * nlev
+    zz = lambda *sh, dt=torch.float64: torch.zeros(sh, dtype=dt, device=dev)
+    dout = dict(cb1=zz(nl, 4), scal=zz(nl, 13), ph_rat=zz(nl, 47), air=zz(nl), h2o=zz(nl), cvv=zz(nl, 4),
+                mech=zz(nl, dt=torch.int32), layers=zz(3, nl, dt=torch.int64), count=zz(3, dt=torch.int64))
+    advr, xadvd = torch.from_numpy(adv_row).to(dev), t(xadv)
+    l0 = drv.launch_count()
+    ms = timeit(lambda: drv.layers_device(cfg, dvd["u0"], dvd["t"], dvd["p"], dvd["rho"], dvd["cm3"], dvd["am3"], dvd["xm1"],
+                                          dvd["conv2"], dvd["cm"], dvd["cloud"], dvd["photol_j"], dout, advr, xadvd,
+                                          dvd["s1"], dvd["s3"]))
+    by = nl * ((6 + 2 * 4 + 2 * 47) * 8 + 4 * 4 + 2 * (93 + 24) * 8 + (4 + 13 + 47 + 2 + 4) * 8 + 4 + 4 + 8)
+    res["driver"] = {"metric": "kpp_driver_layers_per_s", "value": nl * world / (ms * 1e-3), "unit": "layers/s",
+                     "layers_per_gpu": nl, "ms_per_step": ms, "gpu_launches": int(drv.launch_count() - l0),
+                     "layers_by_mechanism": [int(x) for x in dout["count"].cpu().numpy()],
+                     "roofline": {"bound": "hbm", "kernel": "driver_layer_kernel + clip / list kernels", "achieved": by / (ms * 1e-3) * 1e-9,
+                                  "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"],
+                                  "peak_source": peak_src, "traffic": None,
+                                  "note": "algorithmic bytes per layer = inputs (6 scalars, conv2, cm, cloud, two levels of photol_j) + s1 / s3 "
+                                          "read and written by the clip + the output rows + mech read twice by the list kernels = %d B" % (by // nl)}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        m = min(ncd_, 200)
+        cut = {k: (v[:m] if k not in ("detw", "deta") else v) for k, v in dcol.items()}
+        reps, t1 = 0, time.perf_counter()
+        while time.perf_counter() - t1 < 2.0:
+            dvo.layers(cfg, cut["u0"], cut["t"], cut["p"], cut["rho"], cut["cm3"], cut["am3"], cut["xm1"], cut["conv2"], cut["cm"],
+                       cut["cloud"], cut["photol_j"], adv_row, xadv, cut["s1"], cut["s3"])
+            reps += 1
+        dt = time.perf_counter() - t1
+        res["driver"]["cpu_baseline"] = {"value": m * nlev * reps / dt, "unit": "layers/s", "cores": 1, "kind": "port",
+                                         "sample": "%d x %d layers, numpy restatement (vectorised over layers), %.1f s" % (reps, m * nlev, dt)}
+    del dvd, dout, dcol
     # ---- gather / scatter halves of aer_drive on device-resident model arrays (rows a14 / a15) ----
     from mistra_b200 import drive
     from mistra_b200.mechgen import mech as mechmod
