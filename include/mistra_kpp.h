@@ -157,11 +157,12 @@ int64_t mistra_kpp_launch_count_variant(int variant);
  * contract; bit-identical in the strict build).  Which cells are handed over depends on their own step count only, so
  * results do not depend on timing.  steps = -1 (default): 12 for aer when the library chose the kernel by the batch
  * size, off when a variant is pinned, and for gas / tot; 0 = off.  MISTRA_KPP_HANDOFF=<steps> in the environment sets
- * it for aer.  Applies to mistra_kpp_integrate_device (the hand-off pass runs once, after the last chunk of the call);
- * the host-buffer entries recycle their device staging per chunk and do not hand cells over.  Returns 0 or a
- * negative MISTRA_KPP_E* code. */
+ * it for aer.  The hand-off pass runs once per call, after the last chunk (mistra_kpp_integrate_device,
+ * mistra_kpp_integrate, mistra_kpp_integrate_rates, mistra_kpp_integrate_multi); the host-buffer entries then put the
+ * final rows of the handed-over cells in place on the host (mistra_kpp_integrate_rates keeps RCONST of the whole batch
+ * in device memory for it).  Returns 0 or a negative MISTRA_KPP_E* code. */
 int mistra_kpp_set_handoff(int mech, int steps);
-/* Cells the last mistra_kpp_integrate_device call on the current device handed over (synchronises with the device). */
+/* Cells the last integration call on the current device handed over (synchronises with the device). */
 int64_t mistra_kpp_handoff_count(void);
 
 /* Release what the KPP integrators hold on every device they ran on: lane workspaces, on-chip instruction tables,

@@ -47,8 +47,10 @@ struct DeviceState {
   int num_sm = 0;
   cudaStream_t stream = nullptr;
   unsigned long long *counter = nullptr;   // [3]: one cell counter per pipeline slot, [2]: the hand-off pass
-  char *handoff = nullptr;                 // mistra_kpp_integrate_device: deferred-cell count and list, (T, H) per cell, spare statistics
+  char *handoff = nullptr;                 // deferred-cell count and list, (T, H) per cell, spare statistics of a call
   size_t handoff_bytes = 0;
+  char *fix_dev = nullptr, *fix_host = nullptr;   // host-buffer entries: results of the handed-over cells, compact (device / pinned)
+  size_t fix_bytes = 0;
   MechState mech[3];
   // device staging for the host-buffer entry
   void *d_stage = nullptr;
@@ -385,6 +387,71 @@ int launch_handoff_pass(DeviceState &d, int mech, int64_t ncell, const double *d
   return 0;
 }
 
+// Host-buffer entries: the per-chunk copies have taken the handed-over cells home in their intermediate state; their
+// final rows are gathered into a compact block, copied once and put in place on the host.
+__global__ void handoff_gather_kernel(const long long *__restrict__ list, long long count, int nvar, const double *__restrict__ var,
+                                      const int32_t *__restrict__ ierr, const int32_t *__restrict__ stats,
+                                      const double *__restrict__ hexit, const double *__restrict__ texit,
+                                      double *__restrict__ cvar, double *__restrict__ chx, double *__restrict__ ctx,
+                                      int32_t *__restrict__ cst, int32_t *__restrict__ cie)
+{
+  for (long long i = blockIdx.x; i < count; i += gridDim.x) {
+    const long long c = list[i];
+    for (int j = threadIdx.x; j < nvar; j += blockDim.x) cvar[i * nvar + j] = var[c * nvar + j];
+    if (threadIdx.x < 8 && stats) cst[i * 8 + threadIdx.x] = stats[c * 8 + threadIdx.x];
+    if (threadIdx.x == 0) {
+      if (ierr) cie[i] = ierr[c];
+      if (hexit) chx[i] = hexit[c];
+      if (texit) ctx[i] = texit[c];
+    }
+  }
+}
+
+// st has been synchronised (pass 2 done) and so has the D2H stream (the per-chunk rows are home).
+int handoff_fixup_host(DeviceState &d, const KppMechInfo *mi, int64_t ncell, const Handoff &ho, const double *d_var,
+                       const int32_t *d_ie, const int32_t *d_st, const double *d_hx, const double *d_tx, double *var,
+                       int32_t *ierr, int32_t *stats, double *hexit, double *texit, cudaStream_t st)
+{
+  unsigned long long cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, ho.count, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (cnt == 0) return 0;
+  const size_t n = (size_t)cnt, nvar = (size_t)mi->nvar;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_hx = al(n * nvar * 8), o_tx = o_hx + al(n * 8), o_st = o_tx + al(n * 8), o_ie = o_st + al(n * 32),
+               o_ls = o_ie + al(n * 4), total = o_ls + al(n * 8);
+  if (d.fix_bytes < total) {
+    if (d.fix_dev) cudaFree(d.fix_dev);
+    if (d.fix_host) cudaFreeHost(d.fix_host);
+    d.fix_dev = d.fix_host = nullptr; d.fix_bytes = 0;
+    CK(cudaMalloc(&d.fix_dev, total));
+    CK(cudaHostAlloc(&d.fix_host, total, cudaHostAllocPortable));
+    d.fix_bytes = total;
+  }
+  char *g = d.fix_dev;
+  handoff_gather_kernel<<<(unsigned)(n < 4096 ? n : 4096), 128, 0, st>>>(
+      ho.list, (long long)cnt, mi->nvar, d_var, ierr ? d_ie : nullptr, stats ? d_st : nullptr, hexit ? d_hx : nullptr,
+      texit ? d_tx : nullptr, (double *)g, (double *)(g + o_hx), (double *)(g + o_tx), (int32_t *)(g + o_st), (int32_t *)(g + o_ie));
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(g + o_ls, ho.list, n * 8, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(d.fix_host, g, total, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const char *h = d.fix_host;
+  const long long *ls = (const long long *)(h + o_ls);
+  const double *hv = (const double *)h, *hhx = (const double *)(h + o_hx), *htx = (const double *)(h + o_tx);
+  const int32_t *hst = (const int32_t *)(h + o_st), *hie = (const int32_t *)(h + o_ie);
+  for (size_t i = 0; i < n; ++i) {
+    const long long c = ls[i];
+    if (c < 0 || c >= ncell) return fail(MISTRA_KPP_ECUDA, "hand-off list holds a cell index outside the batch");
+    memcpy(var + (size_t)c * nvar, hv + i * nvar, nvar * 8);
+    if (ierr) ierr[c] = hie[i];
+    if (stats) memcpy(stats + (size_t)c * 8, hst + i * 8, 32);
+    if (hexit) hexit[c] = hhx[i];
+    if (texit) texit[c] = htx[i];
+  }
+  return 0;
+}
+
 // ---- compact rate inputs -> the NSPEC-indexed arrays Update_RCONST_x reads (include/mistra_kpp_rates.h) ------------
 __global__ void rates_expand_kernel(double *__restrict__ full, const double *__restrict__ val, const int *__restrict__ idx,
                                     long long nrow, int n, int nspec)
@@ -611,6 +678,12 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
   // both, only pinned ones actually overlap.
   const bool oc = want_onchip(mi, mech, ncell);     // by the size of the whole batch, not of a chunk
   if ((rc = ensure_mech(*d, mech, mi, o ? (o->f32_literals ? 1 : 0) : 1, st, oc))) return rc;
+  Handoff ho, *hop = nullptr;                       // long cells: continued on chip after the last chunk (kpp_batch.h)
+  if (!oc && handoff_steps(mi, mech) > 0) {
+    if ((rc = ensure_mech(*d, mech, mi, o ? (o->f32_literals ? 1 : 0) : 1, st, true))) return rc;
+    if ((rc = handoff_begin(*d, ncell, handoff_steps(mi, mech), &ho, st))) return rc;
+    hop = &ho;
+  }
   const int64_t resident = oc ? (int64_t)d->mech[mech].oc_blocks * mi->oc->slots : (int64_t)d->mech[mech].blocks * KPP_BLOCK;
   int64_t nchunk = ncell / (2 * resident);
   if (nchunk < 1) nchunk = 1;
@@ -644,7 +717,7 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
     rc = launch_device(*d, mech, (int64_t)m, d_rc + o0 * mi->nreact, d_fx + o0 * mi->nfix,
                        d_vr + o0 * mi->nvar, t0, t1, o, ierr ? d_ie + o0 : nullptr,
                        stats ? d_st + o0 * 8 : nullptr, hexit ? d_hx + o0 : nullptr,
-                       texit ? d_tx + o0 : nullptr, ks, slot, oc);
+                       texit ? d_tx + o0 : nullptr, ks, slot, oc, hop, off);
     if (rc) return rc;
     CK(cudaEventRecord(d->ev_k[c], ks));
   }
@@ -662,8 +735,12 @@ int mistra_kpp_integrate(int mech, int64_t ncell, const double *rconst, const do
   }
   CK(cudaEventRecord(d->ev_join, d->s_k2));     // the caller's stream ends after both slots
   CK(cudaStreamWaitEvent(st, d->ev_join, 0));
+  if (hop && (rc = launch_handoff_pass(*d, mech, ncell, d_rc, d_fx, d_vr, t0, t1, o, ierr ? d_ie : nullptr,
+                                       stats ? d_st : nullptr, hexit ? d_hx : nullptr, texit ? d_tx : nullptr, st, ho)))
+    return rc;
   CK(cudaStreamSynchronize(d->s_d2h));
   CK(cudaStreamSynchronize(st));
+  if (hop) return handoff_fixup_host(*d, mi, ncell, ho, d_vr, d_ie, d_st, d_hx, d_tx, var, ierr, stats, hexit, texit, st);
   return 0;
   };
   rc = pipeline();
@@ -717,6 +794,12 @@ int mistra_kpp_integrate_rates(int mech, int64_t ncell, const mistra_rate_inputs
   const bool oc = want_onchip(mi, mech, ncell);
   if ((rc = ensure_mech(*d, mech, mi, o ? (o->f32_literals ? 1 : 0) : 1, st, oc))) return rc;
   if ((rc = ensure_streams(d))) return rc;
+  Handoff ho, *hop = nullptr;                       // long cells: continued on chip after the last chunk (kpp_batch.h)
+  if (!oc && handoff_steps(mi, mech) > 0) {
+    if ((rc = ensure_mech(*d, mech, mi, o ? (o->f32_literals ? 1 : 0) : 1, st, true))) return rc;
+    if ((rc = handoff_begin(*d, ncell, handoff_steps(mi, mech), &ho, st))) return rc;
+    hop = &ho;
+  }
 
   // chunks: as mistra_kpp_integrate, but at most 65536 cells each (the expanded rate arrays are per chunk)
   const int64_t resident = oc ? (int64_t)d->mech[mech].oc_blocks * mi->oc->slots : (int64_t)d->mech[mech].blocks * KPP_BLOCK;
@@ -764,19 +847,23 @@ int mistra_kpp_integrate_rates(int mech, int64_t ncell, const mistra_rate_inputs
   for (int q = 0; q < 6; ++q) { d_val[q] = (double *)p; p += b_val[q]; d_idx[q] = (int *)p; p += b_idx[q]; }
 
   // ---- per-slot scratch: RCONST of a chunk and the NSPEC-indexed arrays (zero outside the lists, set once per call)
-  const size_t c_rc = al((size_t)per * mi->nreact * 8);
+  // (with the hand-off the RCONST of every chunk must survive until the last pass: one block for the whole batch,
+  // laid out behind the two slots, device memory only)
+  const size_t c_rc = hop ? 0 : al((size_t)per * mi->nreact * 8);
+  const size_t c_rc_all = hop ? al(n * mi->nreact * 8) : 0;
   const int nk_full[7] = {1, nkc, nkc, nkc, 2, 1, 1};                 // yhenry yxkmt ykef ykeb yxkmtd yxeq | conc
   size_t c_full[7], c_slot = c_rc;
   for (int q = 0; q < 7; ++q) { c_full[q] = al((size_t)per * nk_full[q] * nspec * 8); c_slot += c_full[q]; }
-  if (d->d_rates_bytes < 2 * c_slot) {
+  if (d->d_rates_bytes < 2 * c_slot + c_rc_all) {
     CK(cudaDeviceSynchronize());
     if (d->d_rates) cudaFree(d->d_rates);
     d->d_rates = nullptr;
     d->d_rates_bytes = 0;
-    CK(cudaMalloc(&d->d_rates, 2 * c_slot));
-    d->d_rates_bytes = 2 * c_slot;
+    CK(cudaMalloc(&d->d_rates, 2 * c_slot + c_rc_all));
+    d->d_rates_bytes = 2 * c_slot + c_rc_all;
   }
   double *s_rc[2], *s_full[2][7];
+  double *d_rc_all = hop ? (double *)((char *)d->d_rates + 2 * c_slot) : nullptr;
   for (int sl = 0; sl < 2; ++sl) {
     char *q = (char *)d->d_rates + sl * c_slot;
     s_rc[sl] = (double *)q; q += c_rc;
@@ -837,10 +924,11 @@ int mistra_kpp_integrate_rates(int mech, int64_t ncell, const mistra_rate_inputs
       in.ycw = rates->ycw ? d_cw + o0 * nkc : nullptr;
       in.ycwd = rates->ycwd ? d_cd + o0 * 2 : nullptr;
       in.f32_literals = rates->f32_literals;
-      if (int r2 = mistra_rconst_update_device(mech, &in, s_rc[slot], ks)) return r2;
-      int r3 = launch_device(*d, mech, (int64_t)m, s_rc[slot], d_fx + o0 * mi->nfix, d_vr + o0 * mi->nvar, t0, t1, o,
+      double *rc_chunk = hop ? d_rc_all + o0 * mi->nreact : s_rc[slot];
+      if (int r2 = mistra_rconst_update_device(mech, &in, rc_chunk, ks)) return r2;
+      int r3 = launch_device(*d, mech, (int64_t)m, rc_chunk, d_fx + o0 * mi->nfix, d_vr + o0 * mi->nvar, t0, t1, o,
                              ierr ? d_ie + o0 : nullptr, stats ? d_st + o0 * 8 : nullptr, hexit ? d_hx + o0 : nullptr,
-                             texit ? d_tx + o0 : nullptr, ks, slot, oc);
+                             texit ? d_tx + o0 : nullptr, ks, slot, oc, hop, off);
       if (r3) return r3;
       CK(cudaEventRecord(d->ev_k[c], ks));
     }
@@ -855,8 +943,13 @@ int mistra_kpp_integrate_rates(int mech, int64_t ncell, const mistra_rate_inputs
     }
     CK(cudaEventRecord(d->ev_join, d->s_k2));
     CK(cudaStreamWaitEvent(st, d->ev_join, 0));
+    if (hop)
+      if (int r4 = launch_handoff_pass(*d, mech, ncell, d_rc_all, d_fx, d_vr, t0, t1, o, ierr ? d_ie : nullptr,
+                                       stats ? d_st : nullptr, hexit ? d_hx : nullptr, texit ? d_tx : nullptr, st, ho))
+        return r4;
     CK(cudaStreamSynchronize(d->s_d2h));
     CK(cudaStreamSynchronize(st));
+    if (hop) return handoff_fixup_host(*d, mi, ncell, ho, d_vr, d_ie, d_st, d_hx, d_tx, var, ierr, stats, hexit, texit, st);
     return 0;
   };
   rc = pipeline();
@@ -1042,6 +1135,9 @@ int mistra_kpp_finalize(void)
     if (d.counter) cudaFree(d.counter);
     if (d.handoff) cudaFree(d.handoff);
     d.handoff = nullptr; d.handoff_bytes = 0;
+    if (d.fix_dev) cudaFree(d.fix_dev);
+    if (d.fix_host) cudaFreeHost(d.fix_host);
+    d.fix_dev = d.fix_host = nullptr; d.fix_bytes = 0;
     for (auto &e : d.ev_slot) if (e) cudaEventDestroy(e);
     if (d.d_stage) cudaFree(d.d_stage);
     if (d.d_rates) cudaFree(d.d_rates);

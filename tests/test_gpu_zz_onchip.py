@@ -181,6 +181,16 @@ def test_handoff_of_long_cells(kpp, cuda_device, oracle):
         assert same.mean() >= 0.95                                   # ... and went on as if nothing had happened
         assert util.rel_err(out[same], plain[same]).max() <= 1e-5
         compare(out, ref, stats, stats_o, ierr, ierr_o, hexit, hexit_o, locked_tol=1e-5, hexit_rtol=1e-4)
+        # the host-buffer entries hand over too (one pass after the last chunk, final rows put in place on the host)
+        h_out, h_ierr, h_stats, h_hexit, h_texit = kpp.integrate(1, rc, ens.fix, ens.var)
+        assert np.array_equal(h_out, out) and np.array_equal(h_stats, stats) and np.array_equal(h_ierr, ierr)
+        assert np.array_equal(h_hexit, hexit) and np.array_equal(h_texit, texit)
+        r1 = kpp.integrate_rates(1, ens.compact_rates(), ens.fix, ens.var)
+        kpp.set_handoff(1, 0)
+        r0 = kpp.integrate_rates(1, ens.compact_rates(), ens.fix, ens.var)
+        kpp.set_handoff(1, 12)
+        assert np.array_equal(r1[1], r0[1]) and (r1[2] == r0[2]).all(axis=1).mean() >= 0.95
+        assert util.rel_err(r1[0], r0[0]).max() <= 1e-4 and util.rel_err(r1[0], ref).max() <= util.RTOL
         # strict build: both kernels reproduce the reference order, so the hand-off must be invisible
         kpp.set_handoff(1, 12, strict=True)
         outs, ierrs, statss, hexits, _ = run(rc, ens.fix, ens.var, strict=True)
