@@ -94,3 +94,64 @@ def test_two_rank_gloo_column_operators_equal_single_process(tmp_path):
     assert [int(p["n"]) for p in parts] == [4, 3]
     for i, r in enumerate(ref):
         assert np.array_equal(np.concatenate([p["o%d" % i] for p in parts]), r)
+
+
+def _settling_inputs(total_cols):
+    from mistra_b200 import kon, sed
+    g = kon.kon_grid(nka=8, nkt=9)
+    d = sed.synthetic_columns(g, total_cols, n=30, nf=20, seed=23, j2=5, j6=3, populated=0.4)
+    return g, d
+
+
+def _driver_inputs(total_cols):
+    from mistra_b200 import driver
+    d = driver.synthetic_columns(total_cols, 16, 12, 4, 7, 3, 29)
+    cfg = dict(nf=12, halo=True, iod=False, lpBuys13_0D=False, neula=0, box=False, n_bl=2, kinv=9, dt_ch=10.0)
+    return cfg, d, np.array([2, -1, 5], dtype=np.int32), np.array([1e-9, 1e-9, -2e-10])
+
+
+def _driver_call(fn, cfg, d, adv_row, xadv, sl=slice(None)):
+    return fn(cfg, *[d[k][sl] for k in ("u0", "t", "p", "rho", "cm3", "am3", "xm1", "conv2", "cm", "cloud", "photol_j")],
+              adv_row, xadv, d["s1"][sl], d["s3"][sl])
+
+
+def _worker_settling(rank, world, port, total_cols, outdir):
+    """sedp / sedl and the layer loop of kpp_driver shard by whole columns as well; the per-rank lists of layers per
+    mechanism become the global ones by adding the rank's first layer row."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from mistra_b200 import shard
+    from oracle import driver_oracle as dvo, sed_oracle as sdo
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    first, n = shard.column_block(total_cols, world, rank)
+    sl = slice(first, first + n)
+    g, d = _settling_inputs(total_cols)
+    ff, dg = sdo.sedp(g, 10.0, 20, d["detw"], d["deta"], d["t"][sl], d["p"][sl], d["vd"][sl], d["ff"][sl], d["diag"][sl])
+    s1 = sdo.sedl(10.0, 20, 3, d["detw"], d["deta"], d["t"][sl], d["p"][sl], d["rc"][sl], d["vt"][sl], d["vdm"][sl], d["sl1"][sl])
+    cfg, dd, adv_row, xadv = _driver_inputs(total_cols)
+    o = _driver_call(dvo.layers, cfg, dd, adv_row, xadv, sl)
+    nlev = dd["t"].shape[1]
+    np.savez(os.path.join(outdir, "sed%d.npz" % rank), ff=ff, dg=dg, sl1=s1, mech=o["mech"], cb1=o["cb1"], scal=o["scal"],
+             **{"lay%d" % m: o["layers"][m] + first * nlev for m in range(3)})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_settling_and_driver_equal_single_process(tmp_path):
+    from oracle import driver_oracle as dvo, sed_oracle as sdo
+    total_cols, world = 5, 2
+    mp.spawn(_worker_settling, args=(world, _free_port(), total_cols, str(tmp_path)), nprocs=world, join=True)
+    g, d = _settling_inputs(total_cols)
+    ff, dg = sdo.sedp(g, 10.0, 20, d["detw"], d["deta"], d["t"], d["p"], d["vd"], d["ff"], d["diag"])
+    s1 = sdo.sedl(10.0, 20, 3, d["detw"], d["deta"], d["t"], d["p"], d["rc"], d["vt"], d["vdm"], d["sl1"])
+    cfg, dd, adv_row, xadv = _driver_inputs(total_cols)
+    o = _driver_call(dvo.layers, cfg, dd, adv_row, xadv)
+    parts = [np.load(os.path.join(str(tmp_path), "sed%d.npz" % r)) for r in range(world)]
+    cat = lambda k: np.concatenate([p[k] for p in parts])
+    assert np.array_equal(cat("ff"), ff) and np.array_equal(cat("dg"), dg) and np.array_equal(cat("sl1"), s1)
+    assert (ff != d["ff"]).any()
+    assert np.array_equal(cat("mech"), o["mech"]) and np.array_equal(cat("cb1"), o["cb1"]) and np.array_equal(cat("scal"), o["scal"])
+    for m in range(3):
+        assert np.array_equal(cat("lay%d" % m), o["layers"][m])
